@@ -1,0 +1,92 @@
+"""ctypes binding of libawqk.so (the C ABI declared in include/awqk.h).
+
+The library is built in-tree by ``awq-converter_b200/build.py`` (``__graft_entry__.build()``).
+Loading fails loudly when it is missing: there is no fallback implementation."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libawqk.so")
+
+BF16, FP16, FP32, FP64 = 0, 1, 2, 3
+ARITH_NATIVE, ARITH_FP32 = 0, 1
+
+_lock = threading.Lock()
+_lib = None
+
+_i64, _int, _vp = C.c_int64, C.c_int, C.c_void_p
+
+# name -> (restype, argtypes); must list every function include/awqk.h declares
+SIGNATURES = {
+    "awqk_version": (_int, []),
+    "awqk_error_string": (C.c_char_p, [_int]),
+    "awqk_last_cuda_error": (C.c_char_p, []),
+    "awqk_group_quant": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp,
+                                _vp, _vp]),
+    "awqk_group_quant_path": (_int, [_int, _i64, _i64, _int, _int, _int, _vp]),
+    "awqk_dequant": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp, _vp]),
+    "awqk_dequant_packed": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
+    "awqk_bf16_to_fp16": (_int, [_vp, _vp, _i64, _vp]),
+    "awqk_abs_colsum": (_int, [_vp, _int, _i64, _i64, _vp, _vp]),
+    "awqk_alpha_grid": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp]),
+    "awqk_fakequant_delta": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _vp, _int, _vp, _vp]),
+    "awqk_sqerr_gemm": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp]),
+    "awqk_pipe_create": (_int, [_int, C.c_size_t, C.POINTER(_vp)]),
+    "awqk_pipe_destroy": (None, [_vp]),
+    "awqk_pipe_quant_host": (_int, [_vp, _vp, _int, _i64, _i64, _int, _int, _int, _int, _vp, _vp, _vp,
+                                    _vp, _vp]),
+    "awqk_pipe_sync": (_int, [_vp]),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """The loaded library (loaded once; thread-safe)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NativeError(
+                        f"{LIB_PATH} not found: build it with `python awq-converter_b200/build.py` "
+                        "(or __graft_entry__.build()).  awq_quantizer has no CPU fallback.")
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "awqk call") -> None:
+    if rc == 0:
+        return
+    L = lib()
+    msg = L.awqk_error_string(rc).decode()
+    detail = L.awqk_last_cuda_error().decode() if rc == -3 else ""
+    raise NativeError(f"{what} failed: {msg} ({rc})" + (f": {detail}" if detail else ""))
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+    table = {torch.bfloat16: BF16, torch.float16: FP16, torch.float32: FP32, torch.float64: FP64}
+    if torch_dtype not in table:
+        raise ValueError(f"Unsupported floating point dtype for the B200 kernels: {torch_dtype}")
+    return table[torch_dtype]
+
+
+def ptr(t) -> int:
+    """device/host address of a tensor (None -> NULL)"""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,218 @@
+"""AWQQuantizer -- same class, constructor, methods and result layout as the reference
+(src/awq_quantizer/quantization/awq.py:24-539), with the per-group Python loops replaced by the
+sm_100a kernels behind include/awqk.h.
+
+What is kept bit-for-bit (checked in tests/ against the reference's own outputs):
+  * ``quantize(t)``   -> {'tensor_q' int32 (t.shape), 'scales' fp16 [C,G], 'zero_points' int32 [C,G],
+                          'bits', 'group_size', 'symmetric'} on CPU            (awq.py:376-416)
+  * arithmetic in the dtype of ``t`` (bf16 in -> bf16-rounded ops, ...)        (awq.py:192-248)
+  * zero padding of ragged rows, 1-D / N-D handling, the numel < group_size bypass with [C]-shaped
+    or 0-d scales                                                              (awq.py:297-339)
+  * ``dequantize`` incl. its fp16 multiply and its IndexError on bypass dicts  (awq.py:459-539)
+  * ``quantize_model`` log-and-skip semantics                                  (awq.py:435-457)
+  * ValueError texts of parameter validation                                   (awq.py:95-112)
+
+What is added (opt-in; defaults reproduce the reference):
+  * ``arith='fp32'``            fp32 arithmetic == reference on ``t.float()``
+  * ``quantize(t, pack=True)``  adds 'qweight' / 'qzeros' (8 nibbles per int32)
+  * ``quantize(t, activations=X)``  activation-aware alpha search (tcgen05 kernels), see search.py
+
+What is deliberately different: there is NO CPU execution path.  The reference silently falls back
+to CPU when CUDA is missing (awq.py:76-77); here ``quantize`` raises instead.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .. import _native as N
+from ..utils.logger import get_logger
+
+
+class AWQQuantizer:
+    def __init__(
+        self,
+        bits: int = 4,
+        group_size: int = 128,
+        symmetric: bool = True,
+        zero_point: str = "minmax",
+        percentile: float = 0.99,
+        scale_method: str = "mse",
+        per_channel: bool = True,
+        device: Optional[str] = None,
+        logger_name: str = "awq_quantizer",
+        logger_level: str = "INFO",
+        logger_to_file: bool = False,
+        logger_file_path: Optional[str] = None,
+        *,
+        arith: str = "native",
+        n_grid: int = 20,
+    ):
+        self.bits = bits
+        self.group_size = group_size
+        self.symmetric = symmetric
+        self.zero_point = zero_point
+        self.percentile = percentile
+        self.scale_method = scale_method
+        self.per_channel = per_channel
+        self.arith = arith
+        self.n_grid = n_grid
+        # awq.py:70-73: default device is CUDA.  (No silent CPU downgrade here.)
+        self.device = "cuda" if device is None else device
+        self.logger = get_logger(name=logger_name, level=logger_level, to_file=logger_to_file,
+                                 file_path=logger_file_path)
+        self._validate_parameters()
+        self.qmin, self.qmax = self._calculate_qmin_qmax()
+        self.logger.info(
+            f"Initialized AWQ Quantizer with bits={bits}, group_size={group_size}, symmetric={symmetric}")
+        self.logger.info(f"Quantization range: [{self.qmin}, {self.qmax}]")
+
+    # ------------------------------------------------------------------ awq.py:95-128
+    def _validate_parameters(self) -> None:
+        if self.bits not in [4, 8]:
+            raise ValueError(f"Unsupported bit width: {self.bits}. Supported: 4, 8.")
+        if self.group_size <= 0 or not isinstance(self.group_size, int):
+            raise ValueError(f"Group size must be a positive integer: {self.group_size}")
+        if self.zero_point not in ["none", "minmax", "percentile"]:
+            raise ValueError(f"Unsupported zero point calibration method: {self.zero_point}")
+        if self.zero_point == "percentile" and (self.percentile <= 0 or self.percentile >= 1):
+            raise ValueError(f"Percentile must be in range (0, 1): {self.percentile}")
+        if self.scale_method not in ["minmax", "mse"]:
+            raise ValueError(f"Unsupported scale calibration method: {self.scale_method}")
+        if self.arith not in ("native", "fp32"):
+            raise ValueError(f"Unsupported arithmetic mode: {self.arith}")
+
+    def _calculate_qmin_qmax(self) -> Tuple[int, int]:
+        if self.symmetric:
+            return -(2 ** (self.bits - 1)), 2 ** (self.bits - 1) - 1
+        return 0, 2 ** self.bits - 1
+
+    # ------------------------------------------------------------------ device plumbing
+    def _cuda_device(self) -> torch.device:
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError(
+                f"device={self.device!r}: this build of awq_quantizer runs only on CUDA (B200, sm_100a); "
+                "it has no CPU implementation")
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA is not available and awq_quantizer (B200 build) has no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        return dev
+
+    def _layout(self, tensor: torch.Tensor):
+        """(rows C, row length K, kernel group size, G, scale shape) per awq.py:297-323."""
+        n = tensor.numel()
+        if n < self.group_size:                                   # bypass, awq.py:297-300
+            if tensor.dim() <= 1 or not self.per_channel:         # awq.py:147-149
+                return 1, n, n, 1, ()
+            C = tensor.shape[0]
+            return C, n // C, n // C, 1, (C,)                     # awq.py:152-171
+        if tensor.dim() <= 1:
+            C, K = 1, n
+        else:
+            C = tensor.shape[0]
+            K = n // C
+        G = math.ceil(K / self.group_size)
+        return C, K, self.group_size, G, (C, G)
+
+    def _check_zero_point_mode(self):
+        if self.zero_point == "percentile":
+            # awq.py:189-190 passes 3 arguments to the 2-argument get_percentile_value -> TypeError
+            raise TypeError("get_percentile_value() takes 2 positional arguments but 3 were given")
+
+    # ------------------------------------------------------------------ awq.py:376-433
+    def quantize(self, tensor: torch.Tensor, *, activations: Optional[torch.Tensor] = None,
+                 pack: bool = False) -> Dict[str, torch.Tensor]:
+        if not isinstance(tensor, torch.Tensor):
+            raise ValueError(f"Expected torch.Tensor, got {type(tensor)}")
+        if not tensor.is_floating_point():
+            raise ValueError(f"Expected floating point tensor, got {tensor.dtype}")
+        dev = self._cuda_device()
+        self._check_zero_point_mode()
+        if tensor.numel() == 0:
+            raise RuntimeError("cannot quantize an empty tensor (reference: min() of an empty tensor)")
+        if activations is not None:
+            from .search import quantize_with_search
+            return quantize_with_search(self, tensor, activations, dev, pack=pack)
+
+        w = tensor.to(dev, non_blocking=True).contiguous()
+        out = self._quantize_device(w, pack=pack)
+        result = {
+            "tensor_q": out["tensor_q"].cpu(),
+            "scales": out["scales"].cpu(),
+            "zero_points": out["zero_points"].cpu(),
+            "bits": torch.tensor(self.bits, dtype=torch.int32),
+            "group_size": torch.tensor(self.group_size, dtype=torch.int32),
+            "symmetric": torch.tensor(self.symmetric, dtype=torch.bool),
+        }
+        if pack:
+            result["qweight"] = out["qweight"].cpu()
+            result["qzeros"] = out["qzeros"].cpu()
+        return result
+
+    def _quantize_device(self, w: torch.Tensor, *, pack: bool = False, unpacked: bool = True,
+                         col_scale: Optional[torch.Tensor] = None,
+                         arith: Optional[str] = None) -> Dict[str, torch.Tensor]:
+        """Device-resident core: ``w`` is a contiguous CUDA tensor; returns CUDA tensors."""
+        dev = w.device
+        C, K, g, G, scale_shape = self._layout(w)
+        arith = self.arith if arith is None else arith
+        per = 32 // self.bits
+        q = torch.empty(w.shape, dtype=torch.int32, device=dev) if unpacked else None
+        scales = torch.empty((C, G), dtype=torch.float16, device=dev)
+        zps = torch.empty((C, G), dtype=torch.int32, device=dev)
+        qweight = torch.empty((C, -(-K // per)), dtype=torch.int32, device=dev) if pack else None
+        qzeros = torch.empty((C, -(-G // per)), dtype=torch.int32, device=dev) if pack else None
+        N.check(N.lib().awqk_group_quant(
+            N.ptr(w), N.dtype_code(w.dtype), C, K, g, self.bits, int(self.symmetric),
+            N.ARITH_FP32 if arith == "fp32" else N.ARITH_NATIVE,
+            N.ptr(q), N.ptr(qweight), N.ptr(scales), N.ptr(zps), N.ptr(qzeros), N.ptr(col_scale),
+            N.stream_ptr(dev)), "awqk_group_quant")
+        out = {"tensor_q": q, "scales": scales.reshape(scale_shape), "zero_points": zps.reshape(scale_shape)}
+        if pack:
+            out["qweight"] = qweight
+            out["qzeros"] = qzeros
+        return out
+
+    # ------------------------------------------------------------------ awq.py:435-457
+    def quantize_model(self, tensors: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, torch.Tensor]]:
+        quantized = {}
+        for name, tensor in tensors.items():
+            try:
+                self.logger.info(f"Quantizing tensor: {name}")
+                quantized[name] = self.quantize(tensor)
+                self.logger.info(f"Successfully quantized tensor: {name}")
+            except Exception as e:  # reference swallows and logs per tensor (awq.py:453-455)
+                self.logger.error(f"Error quantizing tensor: {name}, error: {e}")
+                continue
+        return quantized
+
+    # ------------------------------------------------------------------ awq.py:459-539
+    def dequantize(self, quantized_tensor: Dict[str, torch.Tensor]) -> torch.Tensor:
+        dev = self._cuda_device()
+        tensor_q = quantized_tensor["tensor_q"]
+        scales = quantized_tensor["scales"]
+        zero_points = quantized_tensor["zero_points"]
+        group_size = int(quantized_tensor["group_size"].item())
+        if scales.dim() != 2:
+            # the reference indexes scales[c, g] (awq.py:516) -> IndexError on bypass layouts
+            raise IndexError(f"too many indices for tensor of dimension {scales.dim()}")
+        if tensor_q.numel() == 0:
+            return torch.zeros(tensor_q.shape, dtype=torch.float32)
+        if tensor_q.dim() <= 1:
+            C, K = 1, tensor_q.numel()
+        else:
+            C, K = tensor_q.shape[0], tensor_q.numel() // tensor_q.shape[0]
+        G = math.ceil(K / group_size)
+        if tuple(scales.shape) != (C, G) or tuple(zero_points.shape) != (C, G):
+            raise IndexError(f"scales/zero_points shape {tuple(scales.shape)} does not match {(C, G)}")
+        q = tensor_q.to(dev, dtype=torch.int32, non_blocking=True).contiguous()
+        s = scales.to(dev, dtype=torch.float16, non_blocking=True).contiguous()
+        z = zero_points.to(dev, dtype=torch.int32, non_blocking=True).contiguous()
+        out = torch.empty(tensor_q.shape, dtype=torch.float32, device=dev)
+        N.check(N.lib().awqk_dequant(N.ptr(q), N.ptr(s), N.ptr(z), C, K, group_size, N.ptr(out),
+                                     N.stream_ptr(dev)), "awqk_dequant")
+        return out.cpu()

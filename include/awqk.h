@@ -1,0 +1,151 @@
+/*
+ * awqk.h -- C ABI of the B200 (sm_100a) kernels behind AWQ-Converter's quantization hot path.
+ *
+ * The reference (shanefitch/AWQ-Converter) is pure Python: it has no FFI.  The boundary it
+ * does have is the method surface of `AWQQuantizer` (src/awq_quantizer/quantization/awq.py)
+ * and `convert_bf16_to_fp16` (src/awq_quantizer/utils/tensor_utils.py).  Each entry point
+ * below replaces the arithmetic of one of those methods; the Python mirror in
+ * awq-converter_b200/awq_quantizer binds them with ctypes (see INTEGRATION.md for the stub
+ * a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes; no torch / C++ types.  Device pointers unless the name says host.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - return value: 0 = ok, negative = AWQK_E_* (awqk_error_string() names it).  No exceptions,
+ *     no allocation inside (except awqk_pipe_*, which owns its staging buffers), no global
+ *     mutable state: every call is re-entrant and may be issued concurrently from several host
+ *     threads (the reference calls quantize() from a ThreadPoolExecutor, main.py:609-621).
+ *   - the device the pointers live on is made current for the duration of the call.
+ */
+#ifndef AWQK_H_
+#define AWQK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AWQK_VERSION 100
+
+#if defined(__GNUC__)
+#define AWQK_API __attribute__((visibility("default")))
+#else
+#define AWQK_API
+#endif
+
+/* element types of weight tensors */
+enum { AWQK_BF16 = 0, AWQK_FP16 = 1, AWQK_FP32 = 2, AWQK_FP64 = 3 };
+
+/* arithmetic contract (DESIGN.md "arithmetic-dtype contract"):
+ *   NATIVE: every op rounded to the input dtype, as the reference does on a tensor of that
+ *           dtype (awq.py:192-211, 245-248)  -> equals ref.quantize(w)
+ *   FP32  : every op in fp32                 -> equals ref.quantize(w.float())            */
+enum { AWQK_ARITH_NATIVE = 0, AWQK_ARITH_FP32 = 1 };
+
+enum {
+  AWQK_OK = 0,
+  AWQK_E_BADARG = -1,      /* null pointer, non-positive size, unsupported bits/dtype/arith   */
+  AWQK_E_ALIGN = -2,       /* pointer not aligned as documented                                */
+  AWQK_E_CUDA = -3,        /* a CUDA runtime call failed; see awqk_last_cuda_error()           */
+  AWQK_E_UNSUPPORTED = -4, /* combination not implemented (e.g. col_scale with NATIVE)         */
+  AWQK_E_WORKSPACE = -5,   /* workspace missing or too small                                   */
+  AWQK_E_NODEVICE = -6     /* no sm_100 device                                                 */
+};
+
+AWQK_API int awqk_version(void);
+AWQK_API const char* awqk_error_string(int code);
+/* thread-local text of the last CUDA failure seen by this thread ("" if none) */
+AWQK_API const char* awqk_last_cuda_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  fused group quantizer (+ pack).   Replaces AWQQuantizer._quantize_per_group +
+ *     _compute_scale_zp_for_group + _quantize_tensor            (awq.py:286-374,173-213,215-250)
+ *     and the dtype casts of quantize()                          (awq.py:409-412).
+ *
+ *   w          [C, K] row-major, `dtype`; groups of `group_size` run along K; the last group
+ *              of a row is zero-padded (the zeros take part in min/max, awq.py:337-339).
+ *   q_unpacked nullable, int32 [C, K]          -- the reference's `tensor_q`
+ *   q_packed   nullable, uint32 [C, ceil(K*bits/32)]: word j of a row = sum_i (q[8j+i]-qmin) << 4i
+ *              (bits=8: 4 codes per word, << 8i); tail codes are 0.
+ *   scales     fp16 [C, G], G = ceil(K / group_size)  -- the reference's `scales`
+ *   zp         nullable, int32 [C, G]                  -- the reference's `zero_points`
+ *   zp_packed  nullable, uint32 [C, ceil(G*bits/32)], same packing of (zp - qmin) along G
+ *   col_scale  nullable, fp32 [K]: quantize (float(w) * col_scale[k]) instead of w (AWQ
+ *              per-input-channel scaling); requires arith == AWQK_ARITH_FP32.
+ *   bits       4 or 8.  symmetric: qrange [-2^(b-1), 2^(b-1)-1] else [0, 2^b-1] (awq.py:121-128)
+ *
+ *   Non-finite arithmetic follows the reference on x86: a NaN code / zero point becomes
+ *   INT32_MIN (0 in the packed forms).
+ * ------------------------------------------------------------------------------------- */
+AWQK_API int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, int group_size, int bits,
+                     int symmetric, int arith, int32_t* q_unpacked, uint32_t* q_packed,
+                     void* scales_f16, int32_t* zp, uint32_t* zp_packed, const float* col_scale,
+                     void* stream);
+
+/* which kernel awqk_group_quant would pick: 1 = flat fast path, 0 = generic path, <0 error */
+AWQK_API int awqk_group_quant_path(int dtype, int64_t C, int64_t K, int group_size, int bits, int arith,
+                          const void* w);
+
+/* ---------------------------------------------------------------------------------------
+ * K4  group de-quantizer.  Replaces AWQQuantizer.dequantize / _dequantize_tensor
+ *     (awq.py:459-539, 252-284): out = float(fp16_rn(half(q - zp) * scale)), fp32 [C, K].
+ *     Either q_unpacked (int32 [C,K]) or q_packed/zp_packed (+qmin via symmetric/bits) is given.
+ * ------------------------------------------------------------------------------------- */
+AWQK_API int awqk_dequant(const int32_t* q_unpacked, const void* scales_f16, const int32_t* zp, int64_t C,
+                 int64_t K, int group_size, float* out, void* stream);
+AWQK_API int awqk_dequant_packed(const uint32_t* q_packed, const void* scales_f16, const uint32_t* zp_packed,
+                        int64_t C, int64_t K, int group_size, int bits, int symmetric, float* out,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  bf16 -> fp16 (round to nearest even; overflow -> inf; subnormals kept).
+ *     Replaces convert_bf16_to_fp16 (tensor_utils.py:10-22).
+ * ------------------------------------------------------------------------------------- */
+AWQK_API int awqk_bf16_to_fp16(const void* in_bf16, void* out_fp16, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  activation-aware scale search (no reference counterpart; definition = oracle/awq_oracle.py
+ *     search_scales).  See DESIGN.md.  Declared in awqk_search section below once built.
+ * ------------------------------------------------------------------------------------- */
+
+/* column statistic: sum_t |X[t,k]| accumulated in fp64.  X is [T, K] bf16/fp16/fp32.
+ * `colsum` fp64 [K] must be zeroed by the caller (or accumulate over several calls). */
+AWQK_API int awqk_abs_colsum(const void* x, int dtype, int64_t T, int64_t K, double* colsum, void* stream);
+
+/* s_grid[i, k] = normalised clamp((colsum[k]/T)^(i/n_grid), 1e-4), fp32 [n_grid, K].
+ * workspace: 2 * n_grid floats (min / max per grid point). */
+AWQK_API int awqk_alpha_grid(const double* colsum, int64_t T, int64_t K, int n_grid, float* s_grid,
+                    float* workspace_2n, void* stream);
+
+/* dW[i] = bf16( W - dequant(group_quant(W * s_i)) / s_i ), i = 0..n_s-1; fp32 arithmetic.
+ *   w [C,K] bf16/fp16/fp32;  s [n_s, K] fp32;  dw bf16 [n_s, C, K].  K % group_size == 0. */
+AWQK_API int awqk_fakequant_delta(const void* w, int dtype, int64_t C, int64_t K, int group_size, int bits,
+                         int symmetric, const float* s, int n_s, void* dw_bf16, void* stream);
+
+/* err[i] += sum over [T, C] of (X . dW_i^T)^2, tcgen05 bf16 GEMM with fp32 TMEM accumulators and a
+ * fused sum-of-squares epilogue.  X [T,K] bf16, dW [n_s, C, K] bf16, err fp64 [n_s] (zeroed by the
+ * caller).  Requires K % 64 == 0 and 16-byte aligned bases. */
+AWQK_API int awqk_sqerr_gemm(const void* x_bf16, const void* dw_bf16, int64_t T, int64_t C, int64_t K,
+                    int n_s, double* err, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-buffer pipeline (the e2e path): quantize+pack a host-resident weight through chunked,
+ * double-buffered H2D -> K1 -> D2H on private streams.  Host buffers should be pinned
+ * (cudaHostAlloc / torch pin_memory) for the copies to overlap.
+ * ------------------------------------------------------------------------------------- */
+typedef struct awqk_pipe awqk_pipe;
+AWQK_API int awqk_pipe_create(int device, size_t chunk_bytes, awqk_pipe** out);
+AWQK_API void awqk_pipe_destroy(awqk_pipe* p);
+AWQK_API int awqk_pipe_quant_host(awqk_pipe* p, const void* w_host, int dtype, int64_t C, int64_t K,
+                         int group_size, int bits, int symmetric, int arith,
+                         int32_t* q_unpacked_host, uint32_t* q_packed_host, void* scales_f16_host,
+                         int32_t* zp_host, uint32_t* zp_packed_host);
+/* wait for everything queued on the pipe */
+AWQK_API int awqk_pipe_sync(awqk_pipe* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AWQK_H_ */

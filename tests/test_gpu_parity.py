@@ -1,0 +1,268 @@
+"""GPU (B200): the CUDA path, called through the reference-facing Python mirror and the C ABI,
+against (a) the fixtures frozen from the reference, (b) the pinned oracle on seeded inputs,
+(c) size-independent properties at BASELINE.json's full micro-bench size.
+
+Bar: bit-exact for tensor_q / zero_points / qweight / qzeros and for the fp16 scales (NaN payloads
+excepted)."""
+import concurrent.futures as cf
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import awq_oracle as O
+from tests import datagen
+from tests.golden import cases
+from tests.util import assert_quant_equal, assert_same
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def mk(**kw):
+    from awq_quantizer.quantization import AWQQuantizer
+    kw.setdefault("logger_level", "ERROR")
+    kw.setdefault("device", "cuda:0")
+    return AWQQuantizer(**kw)
+
+
+def golden_result(npz, key):
+    return {
+        "tensor_q": torch.from_numpy(npz[key + "/tensor_q"]),
+        "scales": torch.from_numpy(npz[key + "/scales"]).view(torch.float16),
+        "zero_points": torch.from_numpy(npz[key + "/zero_points"]),
+    }
+
+
+def test_small_cases_vs_reference_golden(native_lib, cuda_device):
+    small = np.load(os.path.join(GOLD, "small.npz"))
+    quantizers = {}
+    n = 0
+    for c in cases.small_cases():
+        key = cases.case_key(c)
+        cfg = (c["bits"], c["group_size"], c["symmetric"], c["per_channel"])
+        if cfg not in quantizers:
+            quantizers[cfg] = mk(bits=c["bits"], group_size=c["group_size"], symmetric=c["symmetric"],
+                                 per_channel=c["per_channel"])
+        qz = quantizers[cfg]
+        w = cases.case_input(c)
+        got = qz.quantize(w)
+        want = golden_result(small, key)
+        assert_quant_equal(got, want, key)
+        assert got["tensor_q"].device.type == "cpu" and got["scales"].device.type == "cpu"
+        assert int(got["bits"]) == c["bits"] and int(got["group_size"]) == c["group_size"]
+        assert got["bits"].dtype == torch.int32 and got["symmetric"].dtype == torch.bool
+        assert bool(got["symmetric"]) == c["symmetric"]
+        if key + "/dequant" in small.files:
+            assert_same(qz.dequantize(got), torch.from_numpy(small[key + "/dequant"]), key + "/dequant")
+        else:
+            with pytest.raises(IndexError):
+                qz.dequantize(got)
+        n += 1
+    assert n >= 400
+
+
+def test_special_values_vs_reference_golden(native_lib, cuda_device):
+    special = np.load(os.path.join(GOLD, "special.npz"))
+    for name in cases.special_inputs():
+        for dt in ("bf16", "fp16", "fp32"):
+            for sym in (False, True):
+                key = f"{name}_{dt}_{'sym' if sym else 'asym'}"
+                raw = special[key + "/input"]
+                w = datagen.from_np(raw, dt).view(datagen.DTYPES[dt]) if dt == "fp16" else datagen.from_np(raw, dt)
+                qz = mk(symmetric=sym)
+                got = qz.quantize(w)
+                assert_quant_equal(got, golden_result(special, key), key)
+                assert_same(qz.dequantize(got), torch.from_numpy(special[key + "/dequant"]), key + "/dequant")
+
+
+def test_config0_shapes_digests(native_lib, cuda_device):
+    """test_quantization.py:54-63,132,136-145 shapes; digests of the reference's own outputs."""
+    from awq_quantizer.utils.tensor_utils import convert_bf16_to_fp16
+    with open(os.path.join(GOLD, "medium.json")) as f:
+        med = json.load(f)
+    for c in cases.MEDIUM_CASES:
+        w = cases.medium_input(c)
+        if c["convert_fp16"]:
+            w = convert_bf16_to_fp16(w)
+            assert w.dtype == torch.float16
+        want = med[c["name"]]
+        assert datagen.digest(w) == want["input"], "converted input differs " + c["name"]
+        qz = mk(symmetric=c["symmetric"])
+        r = qz.quantize(w)
+        for k in ("tensor_q", "scales", "zero_points"):
+            assert datagen.digest(r[k]) == want[k], (c["name"], k)
+        assert datagen.digest(qz.dequantize(r)) == want["dequant"], c["name"]
+    with pytest.raises(ValueError):                     # the 100x100 int32 tensor must be rejected
+        mk().quantize(torch.zeros(100, 100, dtype=torch.int32))
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16", "fp32"])
+@pytest.mark.parametrize("sym", [False, True])
+@pytest.mark.parametrize("g", [32, 64, 128])
+@pytest.mark.parametrize("bits", [4, 8])
+def test_flat_path_vs_oracle(native_lib, cuda_device, dt, sym, g, bits):
+    """seeded Llama-like slabs through the flat kernel, both arithmetic modes, packed + unpacked"""
+    w = datagen.weights((96, 4096), dt, datagen.seed_of("flat", dt, sym, g, bits), std=0.02)
+    w[3, :256] = 0.0                                    # all-zero groups
+    w[5, 100] = 3.0                                     # outlier
+    for arith in ("native", "fp32"):
+        qz = mk(bits=bits, group_size=g, symmetric=sym, arith=arith)
+        got = qz.quantize(w, pack=True)
+        want = O.pack_result(O.group_quant_vec(w, bits, g, sym, True, arith=arith))
+        assert_quant_equal(got, want, f"{dt}/{arith}", keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
+
+
+@pytest.mark.parametrize("shape", [(7, 300), (5, 1000), (3, 8 * 128 + 64), (1, 129)])
+def test_generic_path_packed_vs_oracle(native_lib, cuda_device, shape):
+    for dt in ("bf16", "fp32"):
+        for sym in (False, True):
+            w = datagen.weights(shape, dt, datagen.seed_of("gen", shape, dt, sym), offset=0.1)
+            got = mk(symmetric=sym).quantize(w, pack=True)
+            want = O.pack_result(O.group_quant_vec(w, 4, 128, sym, True))
+            assert_quant_equal(got, want, f"{shape}/{dt}", keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
+
+
+def test_magnitude_sweep_vs_oracle(native_lib, cuda_device):
+    """scales from denormal-ish to huge: exercises the exact (non-hoisted) division path switch"""
+    for dt in ("bf16", "fp16", "fp32"):
+        for e in (-30, -20, -12, -6, 0, 4):
+            if dt == "fp16" and e < -20:
+                continue
+            w = datagen.weights((16, 1024), dt, datagen.seed_of("mag", dt, e), std=10.0 ** e)
+            for sym in (False, True):
+                got = mk(symmetric=sym).quantize(w)
+                assert_quant_equal(got, O.group_quant_vec(w, 4, 128, sym, True), f"{dt}/1e{e}/{sym}")
+
+
+def test_offset_groups_vs_oracle(native_lib, cuda_device):
+    """all-positive / all-negative / tiny-range groups (zero point clamps, scale floor)"""
+    base = datagen.weights((32, 2048), "fp32", 99, std=0.02)
+    for off, mul in ((1.0, 1.0), (-1.0, 1.0), (0.5, 1e-6), (100.0, 1e-3), (0.0, 0.0)):
+        for dt in ("bf16", "fp16", "fp32"):
+            w = (base * mul + off).to(datagen.DTYPES[dt])
+            got = mk(symmetric=False).quantize(w)
+            assert_quant_equal(got, O.group_quant_vec(w, 4, 128, False, True), f"{dt}/{off}/{mul}")
+
+
+def test_full_microbench_shape_properties(native_lib, cuda_device):
+    """8192 x 28672 (BASELINE.json configs[4]): row-slice parity vs the oracle, pack/unpack identity,
+    shard invariance (quantizing row blocks separately gives the same bytes), de-quantization bound."""
+    dev = cuda_device
+    C, K, g = 8192, 28672, 128
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    w = (torch.randn((C, K), generator=gen, device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+    for arith in ("native", "fp32"):
+        qz = mk(symmetric=False, arith=arith)
+        full = qz._quantize_device(w, pack=True)
+        rows = torch.tensor([0, 1, 17, 4095, 4096, 8191] + list(range(100, 164)), device=dev)
+        sub = w[rows].cpu()
+        want = O.pack_result(O.group_quant_vec(sub, 4, g, False, True, arith=arith))
+        for k in ("tensor_q", "scales", "zero_points", "qweight", "qzeros"):
+            assert_same(full[k][rows].cpu(), want[k], f"{arith}/{k}")
+        # pack / unpack identity over the whole tensor, on device
+        sh = torch.arange(8, device=dev, dtype=torch.int32) * 4
+        unp = ((full["qweight"].unsqueeze(-1) >> sh) & 0xF).reshape(C, K)
+        assert torch.equal(unp, full["tensor_q"])
+        unz = ((full["qzeros"].unsqueeze(-1) >> sh) & 0xF).reshape(C, -1)[:, : K // g]
+        assert torch.equal(unz, full["zero_points"])
+        del unp, unz
+        # shard invariance: 4 row blocks quantized independently == the full result
+        for b in range(4):
+            sl = slice(b * 2048, (b + 1) * 2048)
+            part = qz._quantize_device(w[sl].contiguous(), pack=True, unpacked=False)
+            assert torch.equal(part["qweight"], full["qweight"][sl])
+            assert torch.equal(part["qzeros"], full["qzeros"][sl])
+            assert torch.equal(part["scales"], full["scales"][sl])
+        # codes in range; error bound |w - (q - zp) * s| <= s/2 (+ rounding slack) on unclamped codes
+        q = full["tensor_q"]
+        assert int(q.min()) >= 0 and int(q.max()) <= 15
+        s = full["scales"].float().repeat_interleave(g, 1)
+        z = full["zero_points"].float().repeat_interleave(g, 1)
+        err = (w.float() - (q.float() - z) * s).abs()
+        assert bool((err <= 0.5 * s * 1.02 + 1e-6).all())
+        del full, q, s, z, err
+    torch.cuda.empty_cache()
+
+
+def test_bf16_to_fp16_exhaustive_and_bulk(native_lib, cuda_device):
+    from awq_quantizer.utils.tensor_utils import convert_bf16_to_fp16
+    gold = np.load(os.path.join(GOLD, "convert.npz"))["fp16_bits"]
+    allbits = torch.arange(65536, dtype=torch.int32).to(torch.int16).view(torch.bfloat16)
+    got = convert_bf16_to_fp16(allbits)
+    assert got.dtype == torch.float16 and got.device.type == "cpu"
+    assert_same(got, torch.from_numpy(gold).view(torch.float16), "bf16->fp16 exhaustive")
+    f32 = torch.ones(4)
+    assert convert_bf16_to_fp16(f32) is f32             # identity on non-bf16 (tensor_utils.py:20-22)
+    # ragged / unaligned lengths, device in -> device out
+    for n in (1, 7, 8, 9, 8191, 8192 * 3 + 5):
+        x = datagen.weights((n,), "bf16", n, std=300.0).to(cuda_device)
+        y = convert_bf16_to_fp16(x)
+        assert y.device == x.device
+        assert_same(y.cpu(), x.cpu().to(torch.float16), f"n={n}")
+        y2 = convert_bf16_to_fp16(x[1:]) if n > 1 else None      # 2-byte-aligned base -> scalar kernel
+        if y2 is not None:
+            assert_same(y2.cpu(), x[1:].cpu().to(torch.float16), f"n={n} unaligned")
+
+
+def test_reentrant_from_thread_pool(native_lib, cuda_device):
+    """main.py:609-621 calls quantize() from ThreadPoolExecutor workers sharing one quantizer"""
+    qz = mk(symmetric=False)
+    ws = [datagen.weights((64, 1024 + 128 * i), "bf16", 500 + i) for i in range(12)]
+    with cf.ThreadPoolExecutor(max_workers=4) as ex:
+        outs = list(ex.map(qz.quantize, ws))
+    for w, got in zip(ws, outs):
+        assert_quant_equal(got, O.group_quant_vec(w, 4, 128, False, True))
+
+
+def test_quantize_model_and_input_not_mutated(native_lib, cuda_device):
+    qz = mk(symmetric=True)
+    w = datagen.weights((8, 256), "bf16", 1)
+    keep = w.clone()
+    out = qz.quantize_model({"a": w, "skip": torch.zeros(3, dtype=torch.int64), "b": w.float()})
+    assert sorted(out) == ["a", "b"]
+    assert torch.equal(w.view(torch.int16), keep.view(torch.int16))
+    assert_quant_equal(out["a"], O.group_quant_vec(w, 4, 128, True, True))
+    nc = datagen.weights((256, 6), "bf16", 2).t()                 # non-contiguous input
+    assert_quant_equal(qz.quantize(nc), O.group_quant_vec(nc.contiguous(), 4, 128, True, True))
+    with pytest.raises(RuntimeError):
+        qz.quantize(torch.zeros(0, 5))
+
+
+def test_fp64_input(native_lib, cuda_device):
+    w = datagen.weights((4, 300), "fp64", 77, offset=0.1)
+    for sym in (False, True):
+        assert_quant_equal(mk(symmetric=sym).quantize(w), O.group_quant_vec(w, 4, 128, sym, True))
+
+
+def test_c_abi_direct_device_pointers(native_lib, cuda_device):
+    """call the C ABI the way a non-Python host would: raw device pointers + stream"""
+    from awq_quantizer import _native as N
+    dev = cuda_device
+    w = datagen.weights((32, 1024), "bf16", 5).to(dev)
+    scales = torch.empty((32, 8), dtype=torch.float16, device=dev)
+    zp = torch.empty((32, 8), dtype=torch.int32, device=dev)
+    qw = torch.empty((32, 128), dtype=torch.int32, device=dev)
+    qz = torch.empty((32, 1), dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream(dev)
+    st.wait_stream(torch.cuda.current_stream(dev))
+    rc = native_lib.awqk_group_quant(w.data_ptr(), N.BF16, 32, 1024, 128, 4, 0, N.ARITH_NATIVE, None,
+                                     qw.data_ptr(), scales.data_ptr(), zp.data_ptr(), qz.data_ptr(), None,
+                                     st.cuda_stream)
+    assert rc == 0
+    st.synchronize()
+    want = O.pack_result(O.group_quant_vec(w.cpu(), 4, 128, False, True))
+    assert_same(qw.cpu(), want["qweight"]); assert_same(qz.cpu(), want["qzeros"])
+    assert_same(scales.cpu(), want["scales"]); assert_same(zp.cpu(), want["zero_points"])
+    # packed de-quantization == unpacked de-quantization == oracle
+    out = torch.empty((32, 1024), dtype=torch.float32, device=dev)
+    assert native_lib.awqk_dequant_packed(qw.data_ptr(), scales.data_ptr(), qz.data_ptr(), 32, 1024, 128, 4, 0,
+                                          out.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert_same(out.cpu(), O.dequant_vec({**want, "group_size": torch.tensor(128)}))
+    # host pointer where a device pointer is expected -> error code, not a crash
+    host = torch.zeros(4, 128, dtype=torch.bfloat16)
+    assert native_lib.awqk_group_quant(host.data_ptr(), N.BF16, 4, 128, 128, 4, 0, 0, None, None,
+                                       scales.data_ptr(), None, None, None, None) < 0

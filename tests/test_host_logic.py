@@ -1,0 +1,85 @@
+"""CPU: the Python mirror of the reference interface -- constructor / validation / layout rules /
+loud failure without a GPU (no CPU fallback)."""
+import pytest
+import torch
+
+from awq_quantizer.quantization import AWQQuantizer
+from awq_quantizer.quantization.awq import AWQQuantizer as AWQQuantizer2
+
+
+def mk(**kw):
+    kw.setdefault("logger_level", "ERROR")
+    return AWQQuantizer(**kw)
+
+
+def test_same_import_paths_as_reference():
+    assert AWQQuantizer is AWQQuantizer2
+
+
+def test_defaults_match_reference_signature():
+    q = mk()
+    assert (q.bits, q.group_size, q.symmetric, q.zero_point, q.percentile, q.scale_method, q.per_channel) == \
+        (4, 128, True, "minmax", 0.99, "mse", True)
+    assert (q.qmin, q.qmax) == (-8, 7)
+    assert (mk(symmetric=False).qmin, mk(symmetric=False).qmax) == (0, 15)
+    assert (mk(bits=8).qmin, mk(bits=8).qmax) == (-128, 127)
+    assert (mk(bits=8, symmetric=False).qmin, mk(bits=8, symmetric=False).qmax) == (0, 255)
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(bits=3), "Unsupported bit width: 3. Supported: 4, 8."),
+    (dict(group_size=0), "Group size must be a positive integer: 0"),
+    (dict(group_size=-4), "Group size must be a positive integer: -4"),
+    (dict(group_size=64.0), "Group size must be a positive integer: 64.0"),
+    (dict(zero_point="foo"), "Unsupported zero point calibration method: foo"),
+    (dict(zero_point="percentile", percentile=1.5), "Percentile must be in range (0, 1): 1.5"),
+    (dict(scale_method="abs"), "Unsupported scale calibration method: abs"),
+])
+def test_validation_messages(kw, msg):
+    with pytest.raises(ValueError) as e:
+        mk(**kw)
+    assert str(e.value) == msg
+
+
+def test_type_errors_precede_device_use():
+    q = mk(device="cuda")
+    with pytest.raises(ValueError, match="Expected torch.Tensor"):
+        q.quantize([1.0, 2.0])
+    with pytest.raises(ValueError, match="Expected floating point tensor"):
+        q.quantize(torch.zeros(100, 100, dtype=torch.int32))   # test_quantization.py:63
+
+
+def test_no_cpu_fallback():
+    q = mk(device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        q.quantize(torch.zeros(4, 128))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mk(device="cuda").quantize(torch.zeros(4, 128))
+        with pytest.raises(RuntimeError):
+            mk(device="cuda").dequantize({"tensor_q": torch.zeros(1, 128, dtype=torch.int32),
+                                          "scales": torch.ones(1, 1, dtype=torch.float16),
+                                          "zero_points": torch.zeros(1, 1, dtype=torch.int32),
+                                          "group_size": torch.tensor(128)})
+
+
+def test_quantize_model_swallows_per_tensor_errors():
+    # awq.py:453-455: errors are logged and the tensor is skipped
+    q = mk(device="cpu")
+    assert q.quantize_model({"a": torch.zeros(4, 128), "b": torch.zeros(3, dtype=torch.int64)}) == {}
+
+
+@pytest.mark.parametrize("shape,pc,expect", [
+    ((768, 3072), True, (768, 3072, 128, 24, (768, 24))),
+    ((768, 3, 768), True, (768, 2304, 128, 18, (768, 18))),
+    ((8, 300), True, (8, 300, 128, 3, (8, 3))),
+    ((300,), True, (1, 300, 128, 3, (1, 3))),
+    ((10, 10), True, (10, 10, 10, 1, (10,))),          # bypass, per-channel -> scales [C]
+    ((10, 10), False, (1, 100, 100, 1, ())),           # bypass, per-tensor -> 0-d scale
+    ((50,), True, (1, 50, 50, 1, ())),
+    ((), True, (1, 1, 1, 1, ())),
+    ((2, 3, 4, 5), True, (2, 60, 60, 1, (2,))),
+])
+def test_layout_rules(shape, pc, expect):
+    q = mk(per_channel=pc)
+    assert q._layout(torch.zeros(shape)) == expect
