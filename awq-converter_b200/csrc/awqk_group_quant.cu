@@ -20,6 +20,8 @@
 // Arithmetic is bit-exact with PyTorch CPU (see awqk_common.cuh): division is IEEE (hoisted
 // reciprocal + residual correction on the fast path, __fdiv_rn otherwise), rounding is
 // half-to-even, no FMA contraction across reference ops.
+#include <cstdlib>
+
 #include "awqk_common.cuh"
 
 namespace awqk {
@@ -446,6 +448,20 @@ static int launch_generic(const InT* w, int64_t C, int64_t K, int g, int64_t G, 
   return AWQK_OK;
 }
 
+// awqk_group_quant_tma.cu
+int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, bool sym, int arith,
+                           uint32_t* q_packed, void* scales, int32_t* zp, uint32_t* zp_packed,
+                           cudaStream_t st);
+
+static bool tma_path_enabled() {
+  // AWQK_FORCE_V1=1 keeps the register-path kernel for A/B measurements (read once, read-only)
+  static const bool enabled = []() {
+    const char* e = getenv("AWQK_FORCE_V1");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return enabled;
+}
+
 }  // namespace awqk
 
 using namespace awqk;
@@ -489,6 +505,13 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
     }
     const int64_t n = C * K;
     int rc;
+    if (bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) && q_unpacked == nullptr &&
+        q_packed != nullptr && col_scale == nullptr && tma_path_enabled() &&
+        (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0) {
+      // K1 v2: TMA-staged, packed-math kernel (the headline int4 pack path)
+      rc = launch_group_quant_tma(w, dtype, n, group_size, sym, arith, q_packed, scales_f16, zp,
+                                  out.zp_packed, st);
+    } else
     // fp32 arithmetic for any input when arith == FP32; otherwise the input's own dtype
     if (dtype == AWQK_BF16) {
       auto p = reinterpret_cast<const __nv_bfloat16*>(w);

@@ -1,0 +1,377 @@
+// K1 v2: the bandwidth path for int4 packing of bf16 / fp16 weights (the headline configuration).
+//
+// Same arithmetic as group_quant_flat (awq.py:173-250 bit-for-bit), restructured so that the SM's
+// issue slots stop being the limiter (v1 measured 26.6 instructions per element, 84 % issue-active,
+// DRAM 32 % -- profiles/r01_k1_v1.md):
+//   * HBM -> shared memory with 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx), a ring of
+//     kStages x 16 KiB per CTA filled by one producer thread; no per-thread load instructions, no
+//     address arithmetic in the consumers, 32-64 KiB per CTA in flight.
+//   * each consumer thread owns 32 consecutive elements (64 B, read as 4 conflict-free LDS.128), so
+//     a group of 128 is 4 lanes (2 shuffle steps), of 64 two lanes, of 32 one lane, and its 32
+//     codes are exactly 4 packed words = one 16-byte store (512 B contiguous per warp).
+//   * min/max on packed bf16x2/fp16x2 words (HMNMX2.NAN), the exact hoisted IEEE division as
+//     packed fp32x2 math (FMUL2/FFMA2/FADD2: two elements per issue slot), round-to-integer by a
+//     magic-constant add, clamp + rebase in ONE integer instruction per pair (VIADDMNMX.S16x2.RELU),
+//     nibble merge by one IMAD per pair + 3 PRMT per word.
+// A warp tile is 1024 elements = 8/16/32 groups, i.e. a whole number of packed zero-point words.
+#include "awqk_common.cuh"
+
+namespace awqk {
+
+constexpr int kV2ConsumerWarps = 8;
+constexpr int kV2Threads = (kV2ConsumerWarps + 1) * 32;   // + 1 producer warp
+constexpr int kV2WarpTile = 1024;                         // elements
+constexpr int kV2CtaTile = kV2WarpTile * kV2ConsumerWarps;  // 8192 elements = 16 KiB
+constexpr int kV2Stages = 4;
+constexpr int kV2StageBytes = kV2CtaTile * 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// ---- per-input-type packed helpers ---------------------------------------------------------
+template <typename InT>
+struct Packed;
+
+template <>
+struct Packed<__nv_bfloat16> {
+  using V2 = __nv_bfloat162;
+  static __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) {
+    V2 r = __hmin2_nan(*reinterpret_cast<V2*>(&a), *reinterpret_cast<V2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+    V2 r = __hmax2_nan(*reinterpret_cast<V2*>(&a), *reinterpret_cast<V2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float2 to_f2(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+  }
+};
+template <>
+struct Packed<__half> {
+  using V2 = __half2;
+  static __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) {
+    V2 r = __hmin2_nan(*reinterpret_cast<V2*>(&a), *reinterpret_cast<V2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+    V2 r = __hmax2_nan(*reinterpret_cast<V2*>(&a), *reinterpret_cast<V2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float2 to_f2(uint32_t w) {
+    return __half22float2(*reinterpret_cast<V2*>(&w));
+  }
+};
+
+__device__ __forceinline__ float v2_fmin_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float v2_fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// pair of clamped unsigned codes (lo | hi << 16), each in [0, 2^BITS - 1], from a packed pair of
+// exact quotients q = x / s.  A selects the reference's arithmetic dtype.
+template <int A, int QMIN>
+struct PairQuant;
+
+template <int QMIN>
+struct PairQuant<AR_F32, QMIN> {
+  // v = q + zp (fp32), t = v + 1.5*2^23 -> low 16 bits of each t hold round(v) as an s16
+  // (|v| < 2^14 guaranteed by the fast-group predicate)
+  float2 zp2, magic2;
+  __device__ __forceinline__ void init(float zp) {
+    zp2 = make_float2(zp, zp);
+    magic2 = make_float2(12582912.0f, 12582912.0f);
+  }
+  __device__ __forceinline__ uint32_t run(float2 q) const {
+    const float2 t = __fadd2_rn(__fadd2_rn(q, zp2), magic2);
+    const uint32_t both = __byte_perm(__float_as_uint(t.x), __float_as_uint(t.y), 0x5410);
+    constexpr uint32_t REBASE = (uint32_t)((-QMIN) & 0xFFFF) * 0x00010001u;
+    return __viaddmin_s16x2_relu(both, REBASE, 0x000F000Fu);
+  }
+};
+template <int QMIN>
+struct PairQuant<AR_BF16, QMIN> {
+  // a = bf16(q); b = bf16(a + zp); t = bf16(b + 192): [128,256) has ulp 1 -> bits = 0x4340 + round(b)
+  __nv_bfloat162 zp2, magic2;
+  __device__ __forceinline__ void init(float zp) {
+    zp2 = __float2bfloat162_rn(zp);
+    magic2 = __float2bfloat162_rn(192.0f);
+  }
+  __device__ __forceinline__ uint32_t run(float2 q) const {
+    const __nv_bfloat162 a = __float22bfloat162_rn(q);
+    const __nv_bfloat162 t = __hadd2(__hadd2(a, zp2), magic2);
+    constexpr uint32_t REBASE = (uint32_t)((-(0x4340 + QMIN)) & 0xFFFF) * 0x00010001u;
+    return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), REBASE, 0x000F000Fu);
+  }
+};
+template <int QMIN>
+struct PairQuant<AR_F16, QMIN> {
+  // fp16: [1024,2048) has ulp 1 -> magic 1536 = 0x6600
+  __half2 zp2, magic2;
+  __device__ __forceinline__ void init(float zp) {
+    zp2 = __float2half2_rn(zp);
+    magic2 = __float2half2_rn(1536.0f);
+  }
+  __device__ __forceinline__ uint32_t run(float2 q) const {
+    const __half2 a = __float22half2_rn(q);
+    const __half2 t = __hadd2(__hadd2(a, zp2), magic2);
+    constexpr uint32_t REBASE = (uint32_t)((-(0x6600 + QMIN)) & 0xFFFF) * 0x00010001u;
+    return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), REBASE, 0x000F000Fu);
+  }
+};
+
+struct V2Out {
+  uint32_t* q_packed;
+  __half* scales;
+  int32_t* zp;          // nullable
+  uint32_t* zp_packed;  // nullable (flat layout only)
+};
+
+template <typename InT, int A, int G, bool SYM>
+__global__ void __launch_bounds__(kV2Threads, 2)
+group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out) {
+  constexpr int LPG = G / 32;            // lanes per group (4, 2, 1)
+  constexpr int GPW = kV2WarpTile / G;   // groups per warp tile (8, 16, 32)
+  constexpr int LPW = 8 * LPG;           // lanes per packed zero-point word (32, 16, 8)
+  constexpr int QMIN = SYM ? -8 : 0;
+  constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + 15);
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kV2Stages * kV2StageBytes);
+  const uint32_t full0 = smem_u32(bars);
+  const uint32_t empty0 = smem_u32(bars + kV2Stages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kV2Stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, kV2ConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kV2ConsumerWarps) {
+    // ================= producer: one thread streams CTA tiles into the ring =================
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kV2Stages;
+        const uint32_t ph = (uint32_t)(it / kV2Stages) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        const int64_t e0 = tile * kV2CtaTile;
+        const int64_t left = n_elems - e0;
+        const uint32_t bytes = (uint32_t)((left < kV2CtaTile ? left : (int64_t)kV2CtaTile) * 2);
+        mbar_expect_tx(full0 + 8 * s, bytes);
+        bulk_g2s(smem_u32(smem + s * kV2StageBytes), w + e0, bytes, full0 + 8 * s);
+      }
+    }
+    return;
+  }
+
+  // ================================ consumers =================================================
+  PairQuant<A, QMIN> pq;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int s = it % kV2Stages;
+    const uint32_t ph = (uint32_t)(it / kV2Stages) & 1u;
+    const int64_t e0 = tile * kV2CtaTile + warp * kV2WarpTile + lane * 32;   // first element of this thread
+    const bool valid = e0 < n_elems;                                         // whole groups are valid or not
+
+    mbar_wait(full0 + 8 * s, ph);
+    // 64 B per thread as 4 x LDS.128.  Register slot c holds 16-byte chunk (c + rot) & 3 of the
+    // thread's span: rotating the chunk order by lane/2 makes every quarter-warp hit 8 distinct
+    // bank groups.  Min/max and the per-word quantization are order independent; only the final
+    // 16-byte store has to rotate the 4 result words back (8 SELs).
+    const int rot = (lane >> 1) & 3;
+    const uint8_t* tbase = smem + s * kV2StageBytes + warp * (kV2WarpTile * 2) + lane * 64;
+    uint32_t wds[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 v = *reinterpret_cast<const uint4*>(tbase + (((c + rot) & 3) << 4));
+      wds[4 * c + 0] = v.x; wds[4 * c + 1] = v.y; wds[4 * c + 2] = v.z; wds[4 * c + 3] = v.w;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * s);   // slot is free as soon as it sits in registers
+    if (!valid) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wds[i] = 0u;
+    }
+
+    // ---- group min / max: packed tree over 16 words, then fold halves, then LPG lanes --------
+    uint32_t mn2 = wds[0], mx2 = wds[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) {
+      mn2 = Packed<InT>::min2(mn2, wds[i]);
+      mx2 = Packed<InT>::max2(mx2, wds[i]);
+    }
+    const float2 mnf = Packed<InT>::to_f2(mn2), mxf = Packed<InT>::to_f2(mx2);
+    float mn = v2_fmin_nan(mnf.x, mnf.y), mx = v2_fmax_nan(mxf.x, mxf.y);
+#pragma unroll
+    for (int m = 1; m < LPG; m <<= 1) {
+      mn = v2_fmin_nan(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, m));
+      mx = v2_fmax_nan(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
+    }
+
+    const FastGroup fg = group_params_fast<A, 4>(mn, mx, SYM, FQMIN, FQMAX);
+    float sc = fg.scale, zp = fg.zp;
+    uint32_t words[4];
+    // tighter than group_params_fast: the packed 16-bit clamp needs round(x/s + zp) inside the
+    // range where the magic-constant add is linear and the s16 rebase cannot wrap
+    //   fp32 : |x|/s < 2^14 (low half of the fp32 magic sum is an s16)
+    //   bf16 : b + 192 must stay in [128, 256)  -> |x|/s < 48
+    //   fp16 : b + 1536 must stay in [1024, 2048) -> |x|/s < 400
+    constexpr float LIM = (A == AR_F32) ? 16384.0f : ((A == AR_BF16) ? 48.0f : 400.0f);
+    const bool fast = fg.ok && (fmaxf(fabsf(mn), fabsf(mx)) < sc * LIM);
+    if (fast) {
+      pq.init(zp);
+      const float2 r2 = make_float2(fg.rcp, fg.rcp);
+      const float2 ns2 = make_float2(-sc, -sc);
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi) {
+        uint32_t b3[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float2 x = Packed<InT>::to_f2(wds[4 * wi + p]);
+          const float2 q0 = __fmul2_rn(x, r2);
+          const float2 e = __ffma2_rn(ns2, q0, x);
+          const float2 q = __ffma2_rn(e, r2, q0);                 // correctly rounded x / s
+          const uint32_t u2 = pq.run(q);                          // (u_lo | u_hi << 16)
+          b3[p] = u2 * 0x01001000u;                               // byte 3 = u_lo | u_hi << 4
+        }
+        const uint32_t lo = __byte_perm(b3[0], b3[1], 0x0073);
+        const uint32_t hi = __byte_perm(b3[2], b3[3], 0x0073);
+        words[wi] = __byte_perm(lo, hi, 0x5410);
+      }
+    } else {
+      const GroupParams gp = group_params<A>(mn, mx, SYM, FQMIN, FQMAX);   // exact IEEE path
+      sc = gp.scale;
+      zp = gp.zp;
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float2 x = Packed<InT>::to_f2(wds[4 * wi + p]);
+          const int c0 = quant_exact<A>(x.x, sc, zp, FQMIN, FQMAX);
+          const int c1 = quant_exact<A>(x.y, sc, zp, FQMIN, FQMAX);
+          const uint32_t u0 = (c0 == INT32_MIN) ? 0u : (uint32_t)(c0 - QMIN);
+          const uint32_t u1 = (c1 == INT32_MIN) ? 0u : (uint32_t)(c1 - QMIN);
+          acc |= (u0 & 15u) << (8 * p);
+          acc |= (u1 & 15u) << (8 * p + 4);
+        }
+        words[wi] = acc;
+      }
+    }
+
+    // ---- stores ------------------------------------------------------------------------------
+    const int zi = f2i_x86(zp);
+    if (valid) {
+      // slot c holds chunk (c + rot) & 3  ->  chunk k sits in slot (k - rot) & 3: rotate left by rot
+      uint32_t o0 = words[0], o1 = words[1], o2 = words[2], o3 = words[3];
+      if (rot & 1) { const uint32_t t = o3; o3 = o2; o2 = o1; o1 = o0; o0 = t; }
+      if (rot & 2) { uint32_t t = o0; o0 = o2; o2 = t; t = o1; o1 = o3; o3 = t; }
+      st_stream16(out.q_packed + (e0 >> 3), make_uint4(o0, o1, o2, o3));
+      if ((lane % LPG) == 0) {
+        const int64_t gidx = e0 / G;
+        out.scales[gidx] = __float2half_rn(sc);
+        if (out.zp != nullptr) out.zp[gidx] = zi;
+      }
+    }
+    if (out.zp_packed != nullptr) {
+      const uint32_t uz = (valid && (lane % LPG) == 0 && zi != INT32_MIN) ? ((uint32_t)(zi - QMIN) & 15u) : 0u;
+      const uint32_t contrib = uz << (4 * ((lane / LPG) & 7));
+      const uint32_t mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
+      const uint32_t wordz = __reduce_or_sync(mask, contrib);
+      if (valid && (lane % LPW) == 0) out.zp_packed[e0 / (8 * G)] = wordz;
+    }
+  }
+}
+
+template <typename InT, int A, int G>
+static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, cudaStream_t st) {
+  const int64_t n_tiles = ceil_div(n, kV2CtaTile);
+  int dev = 0, sms = 0;
+  AWQK_CUDA(cudaGetDevice(&dev));
+  AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t want = (int64_t)sms * 2;
+  const unsigned grid = (unsigned)(n_tiles < want ? n_tiles : want);
+  const size_t smem = (size_t)kV2Stages * kV2StageBytes + 2 * kV2Stages * sizeof(uint64_t);
+  if (sym) {
+    auto k = group_quant_tma<InT, A, G, true>;
+    AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
+  } else {
+    auto k = group_quant_tma<InT, A, G, false>;
+    AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
+  }
+  AWQK_CUDA(cudaGetLastError());
+  return AWQK_OK;
+}
+
+template <typename InT, int A>
+static int launch_v2_g(const InT* w, int64_t n, int g, bool sym, V2Out out, cudaStream_t st) {
+  switch (g) {
+    case 32: return launch_v2_sym<InT, A, 32>(w, n, sym, out, st);
+    case 64: return launch_v2_sym<InT, A, 64>(w, n, sym, out, st);
+    default: return launch_v2_sym<InT, A, 128>(w, n, sym, out, st);
+  }
+}
+
+// Entry used by awqk_group_quant: int4, bf16/fp16 input, packed output only, flat layout
+// (K % g == 0, g in {32,64,128}, 16-byte aligned base).  zp_packed must be null unless G % 8 == 0.
+int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, bool sym, int arith,
+                           uint32_t* q_packed, void* scales, int32_t* zp, uint32_t* zp_packed,
+                           cudaStream_t st) {
+  V2Out out{q_packed, reinterpret_cast<__half*>(scales), zp, zp_packed};
+  if (dtype == AWQK_BF16) {
+    auto p = reinterpret_cast<const __nv_bfloat16*>(w);
+    return arith == AWQK_ARITH_FP32 ? launch_v2_g<__nv_bfloat16, AR_F32>(p, n_elems, g, sym, out, st)
+                                    : launch_v2_g<__nv_bfloat16, AR_BF16>(p, n_elems, g, sym, out, st);
+  }
+  auto p = reinterpret_cast<const __half*>(w);
+  return arith == AWQK_ARITH_FP32 ? launch_v2_g<__half, AR_F32>(p, n_elems, g, sym, out, st)
+                                  : launch_v2_g<__half, AR_F16>(p, n_elems, g, sym, out, st);
+}
+
+}  // namespace awqk

@@ -253,11 +253,12 @@ def bf16_to_fp16(t: torch.Tensor) -> torch.Tensor:
 def pack_rows_u32(codes: torch.Tensor, qmin: int, bits: int = 4) -> torch.Tensor:
     """codes: int32 [R, N] in [qmin, qmax].  u = codes - qmin; word j of a row
     holds u[8j+i] << (4 i), i = 0..7 (bits=4) or u[4j+i] << (8 i), i = 0..3
-    (bits=8); rows are padded with u = 0.  Returned as int32 (two's-complement
+    (bits=8); rows are padded with u = 0; a NaN code (INT32_MIN) packs as u = 0.  Returned as int32 (two's-complement
     view of the uint32 word), shape [R, ceil(N / per_word)]."""
     per = 32 // bits
     R, N = codes.shape
     u = (codes.to(torch.int64) - qmin) & ((1 << bits) - 1)
+    u = torch.where(codes == INT32_MIN, torch.zeros_like(u), u)   # NaN code packs as 0 (definition)
     padn = (-N) % per
     if padn:
         u = F.pad(u, (0, padn))

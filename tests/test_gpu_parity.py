@@ -176,13 +176,16 @@ def test_full_microbench_shape_properties(native_lib, cuda_device):
             assert torch.equal(part["qweight"], full["qweight"][sl])
             assert torch.equal(part["qzeros"], full["qzeros"][sl])
             assert torch.equal(part["scales"], full["scales"][sl])
-        # codes in range; error bound |w - (q - zp) * s| <= s/2 (+ rounding slack) on unclamped codes
+        # codes in range; reconstruction bound: the zero point is rounded (grid shifts by <= s/2) and
+        # edge values are clamped, so |w - (q - zp) * s| <= s (+ slack for bf16-rounded arithmetic)
         q = full["tensor_q"]
         assert int(q.min()) >= 0 and int(q.max()) <= 15
         s = full["scales"].float().repeat_interleave(g, 1)
         z = full["zero_points"].float().repeat_interleave(g, 1)
         err = (w.float() - (q.float() - z) * s).abs()
-        assert bool((err <= 0.5 * s * 1.02 + 1e-6).all())
+        slack = 1.02 if arith == "fp32" else 1.15
+        assert bool((err <= s * slack + 1e-6).all())
+        assert float((err / s).mean()) < 0.3                     # typical error is ~ s/4
         del full, q, s, z, err
     torch.cuda.empty_cache()
 
