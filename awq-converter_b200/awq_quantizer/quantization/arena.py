@@ -1,0 +1,146 @@
+"""Whole-model quantize+pack through ONE flat arena per dtype.
+
+The reference walks the model one tensor at a time (main.py:353-392 -> awq.py:376): move to the
+device, loop over groups, copy back.  Every tensor whose rows are a whole number of groups is, for
+K1, just a flat run of independent groups -- so a model is too, once its tensors sit back to back in
+one buffer with tile-aligned starts.  `HostArena` is that buffer (pinned host memory, 8192-element
+aligned slots = K1's CTA tile); `quantize_arena` streams it through `awqk_pipe_quant_host`
+(chunked H2D -> K1 -> D2H on three streams) with a single C-ABI call per dtype, and hands back
+per-tensor views of the packed output arenas.  No per-tensor launches, no per-tensor allocations.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .. import _native as N
+
+TILE = 8192  # elements; K1's CTA tile and the pipeline's chunk quantum
+
+
+def arena_eligible(shape, dtype, group_size: int, bits: int) -> bool:
+    """flat layout + flat zero-point packing: rows are whole groups and whole packed zero words"""
+    if dtype not in (torch.bfloat16, torch.float16, torch.float32):
+        return False
+    if group_size not in (32, 64, 128):
+        return False
+    n = 1
+    for s in shape:
+        n *= s
+    if n < group_size or n == 0:
+        return False
+    rows = 1 if len(shape) <= 1 else shape[0]
+    k = n // rows
+    per = 32 // bits
+    return k % group_size == 0 and (k // group_size) % per == 0
+
+
+class HostArena:
+    """Pinned host buffers (one per dtype) with a tile-aligned slot per tensor.
+
+    ``specs``: name -> (shape, dtype).  ``views[name]`` is a tensor view into the arena: a loader can
+    read file bytes straight into it (zero copy), or ``from_tensors`` copies existing tensors in."""
+
+    def __init__(self, specs: Dict[str, Tuple[tuple, torch.dtype]], pin: bool = True):
+        self.specs = dict(specs)
+        self.layout: Dict[torch.dtype, List[Tuple[str, int, int]]] = {}   # dtype -> [(name, offset, numel)]
+        self.buffers: Dict[torch.dtype, torch.Tensor] = {}
+        self.views: Dict[str, torch.Tensor] = {}
+        sizes: Dict[torch.dtype, int] = {}
+        for name, (shape, dtype) in self.specs.items():
+            n = int(math.prod(shape)) if len(shape) else 1
+            off = sizes.get(dtype, 0)
+            self.layout.setdefault(dtype, []).append((name, off, n))
+            sizes[dtype] = off + (n + TILE - 1) // TILE * TILE
+        for dtype, total in sizes.items():
+            buf = torch.zeros(total, dtype=dtype, pin_memory=pin and torch.cuda.is_available())
+            self.buffers[dtype] = buf
+            for name, off, n in self.layout[dtype]:
+                self.views[name] = buf[off:off + n].view(self.specs[name][0])
+
+    @classmethod
+    def from_tensors(cls, tensors: Dict[str, torch.Tensor], pin: bool = True) -> "HostArena":
+        arena = cls({k: (tuple(v.shape), v.dtype) for k, v in tensors.items()}, pin=pin)
+        for k, v in tensors.items():
+            arena.views[k].copy_(v)
+        return arena
+
+    def nbytes(self) -> int:
+        return sum(b.numel() * b.element_size() for b in self.buffers.values())
+
+    def payload_bytes(self) -> int:
+        return sum(n * torch.empty((), dtype=dt).element_size() for dt, lay in self.layout.items() for _, _, n in lay)
+
+
+class _PipeHandle:
+    """per-thread, per-device awqk_pipe (the C object is not thread-safe by design)"""
+    _tls = threading.local()
+
+    @classmethod
+    def get(cls, device_index: int, chunk_bytes: int) -> int:
+        pipes = getattr(cls._tls, "pipes", None)
+        if pipes is None:
+            pipes = cls._tls.pipes = {}
+        key = (device_index, chunk_bytes)
+        if key not in pipes:
+            handle = C.c_void_p()
+            N.check(N.lib().awqk_pipe_create(device_index, chunk_bytes, C.byref(handle)), "awqk_pipe_create")
+            pipes[key] = handle
+        return pipes[key]
+
+
+def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: bool, arith: str,
+                   device: torch.device, chunk_bytes: int = 32 << 20, want_zero_points: bool = False,
+                   out: Optional[dict] = None, sync: bool = True) -> Dict[str, Dict[str, torch.Tensor]]:
+    """Quantize+pack every tensor of ``arena``.  Returns name -> {'qweight', 'qzeros', 'scales'
+    (+ 'zero_points'), 'bits', 'group_size', 'symmetric'}; the tensors are views of pinned host output
+    arenas (``out`` may carry those arenas across calls to avoid re-allocating them)."""
+    per = 32 // bits
+    L = N.lib()
+    pipe = _PipeHandle.get(device.index if device.index is not None else torch.cuda.current_device(), chunk_bytes)
+    results: Dict[str, Dict[str, torch.Tensor]] = {}
+    outs = out if out is not None else {}
+    for dtype, buf in arena.buffers.items():
+        n = buf.numel()
+        key = (dtype, n, bits, group_size, want_zero_points)
+        if key not in outs:
+            pin = torch.cuda.is_available()
+            outs[key] = {
+                "q": torch.empty(n // per, dtype=torch.int32, pin_memory=pin),
+                "s": torch.empty(n // group_size, dtype=torch.float16, pin_memory=pin),
+                "zq": torch.empty(n // group_size // per, dtype=torch.int32, pin_memory=pin),
+                "z": torch.empty(n // group_size, dtype=torch.int32, pin_memory=pin) if want_zero_points else None,
+            }
+        o = outs[key]
+        N.check(L.awqk_pipe_quant_host(pipe, buf.data_ptr(), N.dtype_code(dtype), 1, n, group_size, bits,
+                                       int(symmetric), N.ARITH_FP32 if arith == "fp32" else N.ARITH_NATIVE,
+                                       None, o["q"].data_ptr(), o["s"].data_ptr(), N.ptr(o["z"]),
+                                       o["zq"].data_ptr()), "awqk_pipe_quant_host")
+        for name, off, numel in arena.layout[dtype]:
+            shape = arena.specs[name][0]
+            rows = 1 if len(shape) <= 1 else shape[0]
+            k = numel // rows
+            g = k // group_size
+            r = {
+                "qweight": o["q"][off // per:(off + numel) // per].view(rows, k // per),
+                "qzeros": o["zq"][off // group_size // per:(off + numel) // group_size // per].view(rows, g // per),
+                "scales": o["s"][off // group_size:(off + numel) // group_size].view(rows, g),
+                "bits": torch.tensor(bits, dtype=torch.int32),
+                "group_size": torch.tensor(group_size, dtype=torch.int32),
+                "symmetric": torch.tensor(symmetric, dtype=torch.bool),
+            }
+            if want_zero_points:
+                r["zero_points"] = o["z"][off // group_size:(off + numel) // group_size].view(rows, g)
+            results[name] = r
+    if sync:
+        N.check(L.awqk_pipe_sync(pipe), "awqk_pipe_sync")
+    return results
+
+
+def sync_pipe(device: torch.device, chunk_bytes: int = 32 << 20) -> None:
+    pipe = _PipeHandle.get(device.index if device.index is not None else torch.cuda.current_device(), chunk_bytes)
+    N.check(N.lib().awqk_pipe_sync(pipe), "awqk_pipe_sync")

@@ -125,7 +125,7 @@ class AWQQuantizer:
 
     # ------------------------------------------------------------------ awq.py:376-433
     def quantize(self, tensor: torch.Tensor, *, activations: Optional[torch.Tensor] = None,
-                 pack: bool = False) -> Dict[str, torch.Tensor]:
+                 pack: bool = False, keep_unpacked: bool = True) -> Dict[str, torch.Tensor]:
         if not isinstance(tensor, torch.Tensor):
             raise ValueError(f"Expected torch.Tensor, got {type(tensor)}")
         if not tensor.is_floating_point():
@@ -139,9 +139,10 @@ class AWQQuantizer:
             return quantize_with_search(self, tensor, activations, dev, pack=pack)
 
         w = tensor.to(dev, non_blocking=True).contiguous()
-        out = self._quantize_device(w, pack=pack)
+        keep_unpacked = keep_unpacked or not pack
+        out = self._quantize_device(w, pack=pack, unpacked=keep_unpacked)
         result = {
-            "tensor_q": out["tensor_q"].cpu(),
+            "tensor_q": out["tensor_q"].cpu() if keep_unpacked else None,
             "scales": out["scales"].cpu(),
             "zero_points": out["zero_points"].cpu(),
             "bits": torch.tensor(self.bits, dtype=torch.int32),
@@ -151,6 +152,8 @@ class AWQQuantizer:
         if pack:
             result["qweight"] = out["qweight"].cpu()
             result["qzeros"] = out["qzeros"].cpu()
+        if not keep_unpacked:
+            del result["tensor_q"]
         return result
 
     def _quantize_device(self, w: torch.Tensor, *, pack: bool = False, unpacked: bool = True,
@@ -178,16 +181,51 @@ class AWQQuantizer:
         return out
 
     # ------------------------------------------------------------------ awq.py:435-457
-    def quantize_model(self, tensors: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, torch.Tensor]]:
+    def quantize_model(self, tensors, *, pack: bool = False, chunk_bytes: int = 32 << 20):
+        """dict-in / dict-out; a tensor that raises is logged and skipped (awq.py:453-455).
+
+        ``pack=False`` (default): the reference's result layout per tensor (``tensor_q`` int32 ...).
+        ``pack=True``: packed results (``qweight`` / ``qzeros`` / ``scales``).  Every tensor whose rows
+        are whole groups goes through ONE flat arena per dtype and the chunked H2D -> K1 -> D2H
+        pipeline (quantization/arena.py); ``tensors`` may already be a ``HostArena`` (zero-copy)."""
+        if not pack:
+            quantized = {}
+            for name, tensor in tensors.items():
+                try:
+                    self.logger.info(f"Quantizing tensor: {name}")
+                    quantized[name] = self.quantize(tensor)
+                    self.logger.info(f"Successfully quantized tensor: {name}")
+                except Exception as e:
+                    self.logger.error(f"Error quantizing tensor: {name}, error: {e}")
+                    continue
+            return quantized
+
+        from .arena import HostArena, arena_eligible, quantize_arena
+        dev = self._cuda_device()
+        self._check_zero_point_mode()
         quantized = {}
-        for name, tensor in tensors.items():
+        if isinstance(tensors, HostArena):
+            arena, singles = tensors, {}
+            bad = [n for n, (shp, dt) in arena.specs.items() if not arena_eligible(shp, dt, self.group_size, self.bits)]
+            if bad:
+                raise ValueError(f"HostArena holds tensors that need the per-tensor path: {bad[:3]}")
+        else:
+            flat, singles = {}, {}
+            for name, t in tensors.items():
+                if isinstance(t, torch.Tensor) and arena_eligible(tuple(t.shape), t.dtype, self.group_size, self.bits):
+                    flat[name] = t
+                else:
+                    singles[name] = t
+            arena = HostArena.from_tensors(flat) if flat else None
+        if arena is not None:
+            quantized.update(quantize_arena(arena, bits=self.bits, group_size=self.group_size,
+                                            symmetric=self.symmetric, arith=self.arith, device=dev,
+                                            chunk_bytes=chunk_bytes))
+        for name, tensor in singles.items():
             try:
-                self.logger.info(f"Quantizing tensor: {name}")
-                quantized[name] = self.quantize(tensor)
-                self.logger.info(f"Successfully quantized tensor: {name}")
-            except Exception as e:  # reference swallows and logs per tensor (awq.py:453-455)
+                quantized[name] = self.quantize(tensor, pack=True, keep_unpacked=False)
+            except Exception as e:
                 self.logger.error(f"Error quantizing tensor: {name}, error: {e}")
-                continue
         return quantized
 
     # ------------------------------------------------------------------ awq.py:459-539

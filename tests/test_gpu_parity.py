@@ -269,3 +269,63 @@ def test_c_abi_direct_device_pointers(native_lib, cuda_device):
     host = torch.zeros(4, 128, dtype=torch.bfloat16)
     assert native_lib.awqk_group_quant(host.data_ptr(), N.BF16, 4, 128, 128, 4, 0, 0, None, None,
                                        scales.data_ptr(), None, None, None, None) < 0
+
+
+def test_model_arena_pipeline_vs_oracle(native_lib, cuda_device):
+    """quantize_model(pack=True): flat arena + chunked H2D/K1/D2H pipeline (awqk_pipe_quant_host) for
+    tensors whose rows are whole groups / whole zero words, per-tensor path for the rest"""
+    from awq_quantizer.quantization.arena import HostArena
+    shapes = {"a.weight": (256, 1024), "b.weight": (64, 4096), "bias": (1024,), "odd_g4": (96, 512),
+              "ragged": (7, 300), "conv": (32, 2, 1024), "tiny": (10, 10)}
+    tensors = {n: datagen.weights(s, "bf16", datagen.seed_of("arena", n)) for n, s in shapes.items()}
+    tensors["f32.weight"] = datagen.weights((16, 2048), "fp32", 9)
+    tensors["ints"] = torch.zeros(8, 128, dtype=torch.int32)          # logged and skipped
+    for sym, arith in ((False, "native"), (True, "native"), (False, "fp32")):
+        qz = mk(symmetric=sym, arith=arith)
+        # small chunk size -> several chunks per arena, exercising slot reuse in the pipeline
+        out = qz.quantize_model(tensors, pack=True, chunk_bytes=1 << 16)
+        assert sorted(out) == sorted(n for n in tensors if n != "ints")
+        for n, t in tensors.items():
+            if n == "ints":
+                continue
+            if t.numel() < 128:
+                want = O.group_quant_vec(t, 4, 128, sym, True, arith=arith)
+                assert_same(out[n]["scales"], want["scales"], n)
+                continue
+            want = O.pack_result(O.group_quant_vec(t, 4, 128, sym, True, arith=arith))
+            for k in ("qweight", "qzeros", "scales"):
+                assert_same(out[n][k], want[k], f"{n}/{k}/{sym}/{arith}")
+            assert "tensor_q" not in out[n]
+    # zero-copy form: tensors already live in a HostArena
+    eligible = {n: t for n, t in tensors.items() if n in ("a.weight", "b.weight", "bias", "conv")}
+    arena = HostArena.from_tensors(eligible)
+    out = mk(symmetric=False).quantize_model(arena, pack=True)
+    for n, t in eligible.items():
+        want = O.pack_result(O.group_quant_vec(t, 4, 128, False, True))
+        for k in ("qweight", "qzeros", "scales"):
+            assert_same(out[n][k], want[k], f"arena/{n}/{k}")
+
+
+def test_pipe_c_abi_unpacked_and_errors(native_lib, cuda_device):
+    import ctypes as C
+    from awq_quantizer import _native as N
+    w = datagen.weights((64, 2048), "bf16", 31).pin_memory()
+    q = torch.empty((64, 2048), dtype=torch.int32).pin_memory()
+    qp = torch.empty((64, 256), dtype=torch.int32).pin_memory()
+    sc = torch.empty((64, 16), dtype=torch.float16).pin_memory()
+    zp = torch.empty((64, 16), dtype=torch.int32).pin_memory()
+    zq = torch.empty((64, 2), dtype=torch.int32).pin_memory()
+    h = C.c_void_p()
+    assert native_lib.awqk_pipe_create(0, 1 << 16, C.byref(h)) == 0
+    try:
+        rc = native_lib.awqk_pipe_quant_host(h, w.data_ptr(), N.BF16, 64, 2048, 128, 4, 0, N.ARITH_NATIVE,
+                                             q.data_ptr(), qp.data_ptr(), sc.data_ptr(), zp.data_ptr(), zq.data_ptr())
+        assert rc == 0 and native_lib.awqk_pipe_sync(h) == 0
+        want = O.pack_result(O.group_quant_vec(w, 4, 128, False, True))
+        assert_same(q, want["tensor_q"]); assert_same(qp, want["qweight"]); assert_same(sc, want["scales"])
+        assert_same(zp, want["zero_points"]); assert_same(zq, want["qzeros"])
+        # ragged rows are not a flat layout -> explicit error code, never a silent fallback
+        assert native_lib.awqk_pipe_quant_host(h, w.data_ptr(), N.BF16, 64, 2047, 128, 4, 0, 0, None, qp.data_ptr(),
+                                               sc.data_ptr(), None, None) == -4
+    finally:
+        native_lib.awqk_pipe_destroy(h)
