@@ -41,10 +41,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(1000000u)   // suspend-time hint (ns): sleep in hardware, do not spin
       : "memory");
   return ok != 0;
 }
@@ -165,18 +165,18 @@ struct V2Out {
 };
 
 template <typename InT, int A, int G, bool SYM>
-__global__ void __launch_bounds__(kV2Threads, 2)
+__global__ void __launch_bounds__(kV2Threads, 3)
 group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out) {
   constexpr int LPG = G / 32;            // lanes per group (4, 2, 1)
-  constexpr int GPW = kV2WarpTile / G;   // groups per warp tile (8, 16, 32)
   constexpr int LPW = 8 * LPG;           // lanes per packed zero-point word (32, 16, 8)
   constexpr int QMIN = SYM ? -8 : 0;
   constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + 15);
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kV2Stages * kV2StageBytes);
-  const uint32_t full0 = smem_u32(bars);
-  const uint32_t empty0 = smem_u32(bars + kV2Stages);
+  uint32_t full0 = smem_u32(bars);
+  uint32_t empty0 = smem_u32(bars + kV2Stages);
+  asm volatile("" : "+r"(full0), "+r"(empty0));   // keep the shared-window addresses in registers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -190,52 +190,74 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   }
   __syncthreads();
 
+  const int64_t tile0 = blockIdx.x;
+  const int64_t n_iters = (n_tiles > tile0) ? (n_tiles - tile0 + gridDim.x - 1) / gridDim.x : 0;
+
   if (warp == kV2ConsumerWarps) {
     // ================= producer: one thread streams CTA tiles into the ring =================
     if (lane == 0) {
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % kV2Stages;
-        const uint32_t ph = (uint32_t)(it / kV2Stages) & 1u;
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        const int64_t e0 = tile * kV2CtaTile;
-        const int64_t left = n_elems - e0;
-        const uint32_t bytes = (uint32_t)((left < kV2CtaTile ? left : (int64_t)kV2CtaTile) * 2);
-        mbar_expect_tx(full0 + 8 * s, bytes);
-        bulk_g2s(smem_u32(smem + s * kV2StageBytes), w + e0, bytes, full0 + 8 * s);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(w) + tile0 * kV2StageBytes;
+      const int64_t src_stride = (int64_t)gridDim.x * kV2StageBytes;
+      int64_t left = n_elems * 2 - tile0 * kV2StageBytes;          // bytes from this tile to the end
+      uint32_t stage = 0, ph = 1;                                   // first pass over the ring: slots are free
+      for (int64_t it = 0; it < n_iters; ++it) {
+        mbar_wait(empty0 + 8 * stage, ph);
+        const uint32_t bytes = (left < kV2StageBytes) ? (uint32_t)left : (uint32_t)kV2StageBytes;
+        mbar_expect_tx(full0 + 8 * stage, bytes);
+        bulk_g2s(smem_u32(smem) + stage * kV2StageBytes, src, bytes, full0 + 8 * stage);
+        src += src_stride;
+        left -= src_stride;
+        if (++stage == kV2Stages) { stage = 0; ph ^= 1u; }
       }
     }
     return;
   }
 
   // ================================ consumers =================================================
-  PairQuant<A, QMIN> pq;
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int s = it % kV2Stages;
-    const uint32_t ph = (uint32_t)(it / kV2Stages) & 1u;
-    const int64_t e0 = tile * kV2CtaTile + warp * kV2WarpTile + lane * 32;   // first element of this thread
-    const bool valid = e0 < n_elems;                                         // whole groups are valid or not
+  // per-thread invariants; everything that moves from tile to tile advances by a constant stride
+  const uint32_t thr_elem = (uint32_t)warp * kV2WarpTile + (uint32_t)lane * 32u;     // within the CTA tile
+  const int64_t e_first = tile0 * kV2CtaTile + thr_elem;
+  const int64_t e_stride = (int64_t)gridDim.x * kV2CtaTile;
+  // number of iterations in which this thread's 32 elements exist (whole groups are valid or not)
+  const int64_t valid_iters = (n_elems > e_first) ? (n_elems - e_first + e_stride - 1) / e_stride : 0;
+  const int rot = (lane >> 1) & 3;
+  const uint32_t smem_thr = smem_u32(smem) + (uint32_t)warp * (kV2WarpTile * 2) + (uint32_t)lane * 64u;
+  uint32_t ld_off[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    ld_off[c] = smem_thr + (uint32_t)(((c + rot) & 3) << 4);
+    asm volatile("" : "+r"(ld_off[c]));             // (no per-tile re-derivation from SR_CgaCtaId)
+  }
+  uint32_t* q_ptr = out.q_packed + (e_first >> 3);
+  __half* s_ptr = out.scales + e_first / G;
+  int32_t* z_ptr = (out.zp != nullptr) ? out.zp + e_first / G : nullptr;
+  uint32_t* zq_ptr = (out.zp_packed != nullptr) ? out.zp_packed + e_first / (8 * G) : nullptr;
+  const int64_t q_stride = e_stride >> 3, g_stride = e_stride / G, zq_stride = e_stride / (8 * G);
+  const bool leader = (lane % LPG) == 0;
+  const bool zq_writer = (lane % LPW) == 0;
+  const uint32_t zq_shift = 4u * ((uint32_t)(lane / LPG) & 7u);
+  const uint32_t zq_mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
 
-    mbar_wait(full0 + 8 * s, ph);
+  PairQuant<A, QMIN> pq;
+  uint32_t stage = 0, ph = 0;
+  for (int64_t it = 0; it < n_iters; ++it) {
+    const bool valid = it < valid_iters;
+    mbar_wait(full0 + 8 * stage, ph);
     // 64 B per thread as 4 x LDS.128.  Register slot c holds 16-byte chunk (c + rot) & 3 of the
     // thread's span: rotating the chunk order by lane/2 makes every quarter-warp hit 8 distinct
     // bank groups.  Min/max and the per-word quantization are order independent; only the final
     // 16-byte store has to rotate the 4 result words back (8 SELs).
-    const int rot = (lane >> 1) & 3;
-    const uint8_t* tbase = smem + s * kV2StageBytes + warp * (kV2WarpTile * 2) + lane * 64;
     uint32_t wds[16];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const uint4 v = *reinterpret_cast<const uint4*>(tbase + (((c + rot) & 3) << 4));
-      wds[4 * c + 0] = v.x; wds[4 * c + 1] = v.y; wds[4 * c + 2] = v.z; wds[4 * c + 3] = v.w;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(wds[4 * c]), "=r"(wds[4 * c + 1]), "=r"(wds[4 * c + 2]), "=r"(wds[4 * c + 3])
+                   : "r"(ld_off[c] + stage * kV2StageBytes));
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty0 + 8 * s);   // slot is free as soon as it sits in registers
-    if (!valid) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) wds[i] = 0u;
-    }
+    if (lane == 0) mbar_arrive(empty0 + 8 * stage);   // slot is free as soon as it sits in registers
+    if (++stage == kV2Stages) { stage = 0; ph ^= 1u; }
+    // (threads past the end of the tensor compute on stale shared memory and store nothing)
 
     // ---- group min / max: packed tree over 16 words, then fold halves, then LPG lanes --------
     uint32_t mn2 = wds[0], mx2 = wds[0];
@@ -310,20 +332,21 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
       uint32_t o0 = words[0], o1 = words[1], o2 = words[2], o3 = words[3];
       if (rot & 1) { const uint32_t t = o3; o3 = o2; o2 = o1; o1 = o0; o0 = t; }
       if (rot & 2) { uint32_t t = o0; o0 = o2; o2 = t; t = o1; o1 = o3; o3 = t; }
-      st_stream16(out.q_packed + (e0 >> 3), make_uint4(o0, o1, o2, o3));
-      if ((lane % LPG) == 0) {
-        const int64_t gidx = e0 / G;
-        out.scales[gidx] = __float2half_rn(sc);
-        if (out.zp != nullptr) out.zp[gidx] = zi;
+      st_stream16(q_ptr, make_uint4(o0, o1, o2, o3));
+      if (leader) {
+        *s_ptr = __float2half_rn(sc);
+        if (z_ptr != nullptr) *z_ptr = zi;
       }
     }
-    if (out.zp_packed != nullptr) {
-      const uint32_t uz = (valid && (lane % LPG) == 0 && zi != INT32_MIN) ? ((uint32_t)(zi - QMIN) & 15u) : 0u;
-      const uint32_t contrib = uz << (4 * ((lane / LPG) & 7));
-      const uint32_t mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
-      const uint32_t wordz = __reduce_or_sync(mask, contrib);
-      if (valid && (lane % LPW) == 0) out.zp_packed[e0 / (8 * G)] = wordz;
+    if (zq_ptr != nullptr) {
+      const uint32_t uz = (valid && leader && zi != INT32_MIN) ? ((uint32_t)(zi - QMIN) & 15u) : 0u;
+      const uint32_t wordz = __reduce_or_sync(zq_mask, uz << zq_shift);
+      if (valid && zq_writer) *zq_ptr = wordz;
+      zq_ptr += zq_stride;
     }
+    q_ptr += q_stride;
+    s_ptr += g_stride;
+    if (z_ptr != nullptr) z_ptr += g_stride;
   }
 }
 
@@ -333,7 +356,7 @@ static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, cudaStrea
   int dev = 0, sms = 0;
   AWQK_CUDA(cudaGetDevice(&dev));
   AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t want = (int64_t)sms * 2;
+  const int64_t want = (int64_t)sms * 3;
   const unsigned grid = (unsigned)(n_tiles < want ? n_tiles : want);
   const size_t smem = (size_t)kV2Stages * kV2StageBytes + 2 * kV2Stages * sizeof(uint64_t);
   if (sym) {

@@ -9,7 +9,7 @@ g = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 sym = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 mode = sys.argv[4] if len(sys.argv) > 4 else "pack"
 L = N.lib(); dev = torch.device("cuda:0")
-C, K = 8192, 28672
+C, K = int(os.environ.get("ROWS", "8192")), 28672
 bufs = [(torch.randn((C, K), device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16) for _ in range(2)]
 G = K // g
 scales = torch.empty((C, G), dtype=torch.float16, device=dev)

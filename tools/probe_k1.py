@@ -11,7 +11,7 @@ from awq_quantizer import _native as N
 
 L = N.lib()
 dev = torch.device("cuda:0")
-C, K = 8192, 28672
+C, K = int(os.environ.get("ROWS", "8192")), 28672
 n = C * K
 iters = int(os.environ.get("ITERS", "20"))
 bufs = [(torch.randn((C, K), device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16) for _ in range(2)]
