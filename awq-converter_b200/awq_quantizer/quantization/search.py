@@ -1,0 +1,191 @@
+"""Activation-aware per-input-channel scale search (the "AWQ" of the north star).
+
+The reference only cites the AWQ paper (awq.py:1-7); it has no activations, no alpha grid and no
+GEMM.  This module adds them as an opt-in:
+``AWQQuantizer.quantize(W, activations=X)``.  Definition = oracle/awq_oracle.py::search_scales:
+
+    m      = mean_t |X[t, :]|                                  (fp64 accumulation)
+    s_i    = clamp(m ** (i / n_grid), 1e-4) / sqrt(max * min)   i = 0 .. n_grid-1
+    dW_i   = W - dequant(group_quant(W * s_i)) / s_i            the reference's group quantizer, fp32
+    err_i  = mean_{t,c} (X . dW_i^T)^2                          tcgen05 bf16 GEMM, fp32 accumulate
+    best   = argmin err (ties -> smallest i);  result = group_quant(W * s_best) (+ pack)
+
+Everything runs in the sm_100a kernels of csrc/awqk_search.cu; the only host work is the argmin
+over n_grid doubles.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .. import _native as N
+
+_DW_BUDGET_BYTES = 8 << 30    # delta workspace per chunk of the alpha grid
+
+
+def _check(w: torch.Tensor, x: torch.Tensor, group_size: int):
+    if w.dim() != 2:
+        raise ValueError(f"activation-aware search needs a 2-D weight [out, in], got {tuple(w.shape)}")
+    if x.dim() != 2 or x.shape[1] != w.shape[1]:
+        raise ValueError(f"activations must be [tokens, {w.shape[1]}], got {tuple(x.shape)}")
+    if group_size not in (32, 64, 128) or w.shape[1] % group_size != 0:
+        raise ValueError("activation-aware search needs group_size in {32, 64, 128} dividing the input dim")
+    if w.shape[1] % 8 != 0:
+        raise ValueError("input dim must be a multiple of 8")
+
+
+def search_device(w: torch.Tensor, x: torch.Tensor, *, bits: int, group_size: int, symmetric: bool,
+                  n_grid: int = 20, s_grid: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Device-resident search.  ``w`` [C, K] (bf16/fp16/fp32) and ``x`` [T, K] are CUDA tensors.
+    Returns CUDA tensors: 's_grid' fp32 [n_grid, K], 'err_sum' fp64 [n_grid] (sum, not mean),
+    'act_colsum' fp64 [K].  ``s_grid`` may be injected (tests: "given equal scales")."""
+    _check(w, x, group_size)
+    L = N.lib()
+    dev = w.device
+    st = N.stream_ptr(dev)
+    C, K = w.shape
+    T = x.shape[0]
+    colsum = torch.zeros(K, dtype=torch.float64, device=dev)
+    N.check(L.awqk_abs_colsum(N.ptr(x), N.dtype_code(x.dtype), T, K, N.ptr(colsum), st), "awqk_abs_colsum")
+    if s_grid is None:
+        s_grid = torch.empty((n_grid, K), dtype=torch.float32, device=dev)
+        ws = torch.empty(2 * n_grid, dtype=torch.float32, device=dev)
+        N.check(L.awqk_alpha_grid(N.ptr(colsum), T, K, n_grid, N.ptr(s_grid), N.ptr(ws), st), "awqk_alpha_grid")
+    else:
+        s_grid = s_grid.to(device=dev, dtype=torch.float32).contiguous()
+        n_grid = s_grid.shape[0]
+    xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+    xb = xb.contiguous()
+    err = torch.zeros(n_grid, dtype=torch.float64, device=dev)
+    per_alpha = C * K * 2
+    chunk = max(1, min(n_grid, _DW_BUDGET_BYTES // per_alpha))
+    dw = torch.empty((chunk, C, K), dtype=torch.bfloat16, device=dev)
+    for a0 in range(0, n_grid, chunk):
+        n_s = min(chunk, n_grid - a0)
+        N.check(L.awqk_fakequant_delta(N.ptr(w), N.dtype_code(w.dtype), C, K, group_size, bits, int(symmetric),
+                                       s_grid[a0].data_ptr(), n_s, N.ptr(dw), st), "awqk_fakequant_delta")
+        N.check(L.awqk_sqerr_gemm(N.ptr(xb), N.ptr(dw), T, C, K, n_s, err[a0].data_ptr() if a0 else N.ptr(err), st),
+                "awqk_sqerr_gemm")
+    return {"s_grid": s_grid, "err_sum": err, "act_colsum": colsum, "dw_last": dw}
+
+
+def quantize_with_search(qz, tensor: torch.Tensor, activations: torch.Tensor, dev: torch.device, *,
+                         pack: bool = False) -> Dict[str, torch.Tensor]:
+    """``AWQQuantizer.quantize(tensor, activations=...)``: search, then the final group quantization
+    of fp32 (W * s_best) with K1 (col_scale path, fp32 arithmetic)."""
+    w = tensor.to(dev, non_blocking=True).contiguous()
+    x = activations.to(dev, non_blocking=True).contiguous()
+    r = search_device(w, x, bits=qz.bits, group_size=qz.group_size, symmetric=qz.symmetric, n_grid=qz.n_grid)
+    T, C = x.shape[0], w.shape[0]
+    err = (r["err_sum"] / float(T * C)).cpu()
+    best = int(torch.argmin(err))                      # first minimum -> ties go to the smallest alpha
+    s_best = r["s_grid"][best].contiguous()
+    out = qz._quantize_device(w, pack=pack, col_scale=s_best, arith="fp32")
+    result = {
+        "tensor_q": out["tensor_q"].cpu(),
+        "scales": out["scales"].cpu(),
+        "zero_points": out["zero_points"].cpu(),
+        "bits": torch.tensor(qz.bits, dtype=torch.int32),
+        "group_size": torch.tensor(qz.group_size, dtype=torch.int32),
+        "symmetric": torch.tensor(qz.symmetric, dtype=torch.bool),
+        "awq_scale": s_best.cpu(),
+        "alpha": torch.tensor(best / qz.n_grid, dtype=torch.float32),
+        "best_idx": torch.tensor(best, dtype=torch.int32),
+        "search_err": err,
+    }
+    if pack:
+        result["qweight"] = out["qweight"].cpu()
+        result["qzeros"] = out["qzeros"].cpu()
+    return result
+
+
+# ------------------------------------------------------------------------------------------------
+def smoke_check() -> None:
+    """tiny end-to-end search on cuda:0 against the oracle (called by __graft_entry__.smoke)"""
+    from oracle import awq_oracle as O
+    from tests import datagen
+    dev = torch.device("cuda", 0)
+    W = datagen.weights((256, 256), "bf16", 3)
+    X = datagen.activations(192, 256, "bf16", 4)
+    r = search_device(W.to(dev), X.to(dev), bits=4, group_size=128, symmetric=False, n_grid=4)
+    want = O.search_scales(W, X, 4, 128, False, n_grid=4, s_grid=r["s_grid"].cpu())
+    got = (r["err_sum"] / (192 * 256)).cpu()
+    for i in range(4):
+        assert abs(float(got[i]) - want["err"][i]) <= 1e-3 * want["err"][i], (i, float(got[i]), want["err"][i])
+    assert int(torch.argmin(got)) == want["best_idx"]
+
+
+def bench_leg(args, dev, world: int, rank: int, tf_peak: float, peak_kind: str):
+    """bench.py's search leg: every linear of this rank's share of the workload, synthetic
+    activations X[T, K] = N(0,1) * exp(N(0,1)) per channel, n_grid = 20.  Device-resident, CUDA-event
+    timed, max over ranks.  Reports s/model and the GEMM kernel against the bf16 tensor peak."""
+    import torch.distributed as dist
+    from .. import model_shapes as M
+    L = N.lib()
+    g, n_grid, T = args.group_size, 20, args.search_tokens
+    specs = M.workload(args.workload)
+    pool = [(f"r{r}/{name}", shape) for r in range(world) for name, shape, ck in specs if ck is not None]
+    bins = M.partition_lpt([(n, M.numel(s) * T) for n, s in pool], world)     # cost ~ C*K*T
+    mine = [(n, s) for n, s in pool if n in set(bins[rank])]
+    distinct = sorted({tuple(s) for _, s in mine})
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    xs = {}
+    for _, (C, K) in [(None, s) for s in distinct]:
+        if K not in xs:
+            gain = torch.exp(torch.randn(K, generator=gen, device=dev))
+            xs[K] = (torch.randn((T, K), generator=gen, device=dev) * gain).to(torch.bfloat16)
+    ws = {s: (torch.randn(s, generator=gen, device=dev) * 0.02).to(torch.bfloat16) for s in distinct}
+    counts = {s: sum(1 for _, t in mine if tuple(t) == s) for s in distinct}
+
+    def one(shape):
+        return search_device(ws[shape], xs[shape[1]], bits=4, group_size=g, symmetric=args.symmetric, n_grid=n_grid)
+
+    for s in distinct:      # warm-up (also allocates the delta workspace in torch's caching allocator)
+        one(s)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for s in distinct:
+        for _ in range(counts[s]):
+            one(s)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    flops = sum(2.0 * T * s[0] * s[1] * n_grid * counts[s] for s in distinct)
+    if world > 1:
+        t = torch.tensor([ms, flops], device=dev, dtype=torch.float64)
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+        dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        ms, flops = float(t[0]), float(t[1])
+    # the GEMM kernel alone on the largest shape (roofline of the dominant kernel of this leg)
+    big = max(distinct, key=lambda s: s[0] * s[1])
+    C, K = big
+    r = one(big)
+    dw, xb = r["dw_last"], xs[K]
+    n_s = dw.shape[0]
+    err = torch.zeros(n_s, dtype=torch.float64, device=dev)
+    st = N.stream_ptr(dev)
+    for _ in range(2):
+        N.check(L.awqk_sqerr_gemm(N.ptr(xb), N.ptr(dw), T, C, K, n_s, N.ptr(err), st))
+    torch.cuda.synchronize(dev)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        N.check(L.awqk_sqerr_gemm(N.ptr(xb), N.ptr(dw), T, C, K, n_s, N.ptr(err), st))
+    e1.record()
+    torch.cuda.synchronize(dev)
+    gemm_ms = e0.elapsed_time(e1) / reps
+    gemm_tf = 2.0 * T * C * K * n_s / (gemm_ms * 1e-3) / 1e12
+    return {
+        "s_per_model": ms * 1e-3, "tokens": T, "n_grid": n_grid, "linears_per_rank": len(mine),
+        "tflops_executed": flops / (ms * 1e-3) / 1e12,
+        "flops_executed": flops, "flops_survey_formula": flops * (n_grid + 1) / n_grid,
+        "roofline": {"bound": "tensor", "kernel": "sqerr_gemm_kernel (tcgen05, K2)", "achieved": gemm_tf, "peak": tf_peak,
+                     "unit": "TFLOP/s", "frac": gemm_tf / tf_peak, "peak_source": peak_kind + " (sustained bf16)",
+                     "shape": f"T={T} C={C} K={K} n_s={n_s}", "ms_per_launch": gemm_ms, "traffic": None},
+    }

@@ -1,0 +1,553 @@
+// K2: activation-aware alpha search.  No reference counterpart: the definition
+// is oracle/awq_oracle.py::search_scales, which composes the reference's own group quantizer
+// (awq.py:173-250, fp32 arithmetic).
+//
+//   awqk_abs_colsum      sum_t |X[t,k]| in fp64 (exact for bf16 inputs -> order independent)
+//   awqk_alpha_grid      s_i[k] = clamp(m[k]^(i/n), 1e-4) / sqrt(max_k * min_k),  m = colsum / T
+//   awqk_fakequant_delta dW_i = bf16( W - dequant(group_quant(W * s_i)) / s_i )   (bandwidth kernel)
+//   awqk_sqerr_gemm      err_i = sum_{t,c} ( X . dW_i^T )^2   -- the dense contraction:
+//                        tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands staged by TMA into
+//                        128-byte-swizzled shared memory through a 4-stage mbarrier ring, double
+//                        buffered TMEM accumulators, sum-of-squares epilogue fused on tcgen05.ld.
+//
+// err uses the delta form ||X (W - W^)^T||^2 (identical in exact arithmetic to ||X W^T - X W^^T||^2):
+// half the flops, and rounding dW (not W^) to bf16 keeps the relative error of err ~1e-6.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "awqk_common.cuh"
+
+namespace awqk {
+
+// ------------------------------------------------------------------------------------------
+// column statistic
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float abs_as_float(T v);
+template <>
+__device__ __forceinline__ float abs_as_float<__nv_bfloat16>(__nv_bfloat16 v) { return fabsf(__bfloat162float(v)); }
+template <>
+__device__ __forceinline__ float abs_as_float<__half>(__half v) { return fabsf(__half2float(v)); }
+template <>
+__device__ __forceinline__ float abs_as_float<float>(float v) { return fabsf(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+abs_colsum_kernel(const T* __restrict__ x, int64_t Tn, int64_t K, int rows_per_cta, double* __restrict__ colsum) {
+  const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (k >= K) return;
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t t1 = (t0 + rows_per_cta < Tn) ? t0 + rows_per_cta : Tn;
+  double acc = 0.0;
+  for (int64_t t = t0; t < t1; ++t) acc += (double)abs_as_float(x[t * K + k]);
+  atomicAdd(colsum + k, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// alpha grid: pass 1 raw powers + per-alpha min/max, pass 2 normalisation
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+alpha_grid_raw(const double* __restrict__ colsum, int64_t Tn, int64_t K, int n_grid, float* __restrict__ s_grid,
+               unsigned int* __restrict__ mnmx /* [2*n_grid] float bits: min then max */) {
+  const int i = blockIdx.y;
+  const float alpha = (float)((double)i / (double)n_grid);
+  float lmin = __int_as_float(0x7F800000), lmax = 0.0f;
+  for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < K; k += (int64_t)gridDim.x * 256) {
+    const float m = (float)(colsum[k] / (double)Tn);
+    float p;
+    if (i == 0) p = 1.0f;                         // m^0
+    else if (2 * i == n_grid) p = sqrtf(m);       // torch special-cases exponent 0.5
+    else p = powf(m, alpha);
+    p = (p != p) ? p : fmaxf(p, 1e-4f);           // torch.clamp keeps NaN
+    s_grid[(int64_t)i * K + k] = p;
+    lmin = fminf(lmin, p);
+    lmax = fmaxf(lmax, p);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    lmin = fminf(lmin, __shfl_xor_sync(0xFFFFFFFFu, lmin, o));
+    lmax = fmaxf(lmax, __shfl_xor_sync(0xFFFFFFFFu, lmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {                  // all values are positive: uint order == float order
+    atomicMin(mnmx + i, __float_as_uint(lmin));
+    atomicMax(mnmx + n_grid + i, __float_as_uint(lmax));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+alpha_grid_norm(int64_t K, int n_grid, float* __restrict__ s_grid, const unsigned int* __restrict__ mnmx) {
+  const int i = blockIdx.y;
+  const float norm = sqrtf(__fmul_rn(__uint_as_float(mnmx[n_grid + i]), __uint_as_float(mnmx[i])));
+  for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < K; k += (int64_t)gridDim.x * 256)
+    s_grid[(int64_t)i * K + k] = __fdiv_rn(s_grid[(int64_t)i * K + k], norm);
+}
+
+__global__ void alpha_grid_init(int n_grid, unsigned int* mnmx) {
+  const int i = threadIdx.x;
+  if (i < n_grid) {
+    mnmx[i] = 0x7F800000u;
+    mnmx[n_grid + i] = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fake-quant delta: one pass over W for all n_s scale vectors
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 r = ld_stream16(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&f)[8]) {
+  const uint4 r = ld_stream16(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+__device__ __forceinline__ float dq_fmin_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float dq_fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// thread = 8 consecutive elements of a row; group = G/8 adjacent lanes (flat layout, K % G == 0)
+template <typename T, int G, int BITS>
+__global__ void __launch_bounds__(256)
+fakequant_delta_kernel(const T* __restrict__ w, int64_t n_elems, int64_t K, bool sym,
+                       const float* __restrict__ s_grid, int n_s, __nv_bfloat16* __restrict__ dw) {
+  constexpr int LPG = G / 8;
+  const int64_t e0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+  const bool valid = e0 < n_elems;
+  const float qmin = sym ? -(float)(1 << (BITS - 1)) : 0.0f;
+  const float qmax = sym ? (float)((1 << (BITS - 1)) - 1) : (float)((1 << BITS) - 1);
+  float wv[8];
+  if (valid) load8<T>(w + e0, wv);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[i] = 0.0f;
+  }
+  const int64_t k0 = valid ? (e0 % K) : 0;
+#pragma unroll 1
+  for (int a = 0; a < n_s; ++a) {
+    const float* sp = s_grid + (int64_t)a * K + k0;
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __fmul_rn(wv[i], sv[i]);                 // Ws = W * s
+    float mn = x[0], mx = x[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      mn = dq_fmin_nan(mn, x[i]);
+      mx = dq_fmax_nan(mx, x[i]);
+    }
+#pragma unroll
+    for (int m = 1; m < LPG; m <<= 1) {
+      mn = dq_fmin_nan(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, m));
+      mx = dq_fmax_nan(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
+    }
+    const FastGroup fg = group_params_fast<AR_F32, BITS>(mn, mx, sym, qmin, qmax);
+    float sc = fg.scale, zp = fg.zp;
+    float qf[8];
+    if (fg.ok) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v = __fadd_rn(div_hoisted(x[i], sc, fg.rcp), zp);
+        qf[i] = fminf(fmaxf(rintf(v), qmin), qmax);
+      }
+    } else {
+      const GroupParams gp = group_params<AR_F32>(mn, mx, sym, qmin, qmax);
+      sc = gp.scale;
+      zp = gp.zp;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float r = rintf(__fadd_rn(__fdiv_rn(x[i], sc), zp));
+        qf[i] = (r != r) ? r : fminf(fmaxf(r, qmin), qmax);
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      // W^ = ((q - zp) * scale) / s ;  dW = W - W^
+      const float d0 = __fsub_rn(wv[i], __fdiv_rn(__fmul_rn(__fsub_rn(qf[i], zp), sc), sv[i]));
+      const float d1 = __fsub_rn(wv[i + 1], __fdiv_rn(__fmul_rn(__fsub_rn(qf[i + 1], zp), sc), sv[i + 1]));
+      const __nv_bfloat162 b = __floats2bfloat162_rn(d0, d1);
+      o[i / 2] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    if (valid) st_stream16(dw + (int64_t)a * n_elems + e0, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 GEMM with fused sum-of-squares epilogue
+// ------------------------------------------------------------------------------------------
+constexpr int kBM = 128, kBN = 256, kBK = 64;          // CTA tile; UMMA 128 x 256 x 16 (x4 per k-block)
+constexpr int kGStages = 4;
+constexpr int kABytes = kBM * kBK * 2;                 // 16 KiB
+constexpr int kBBytes = kBN * kBK * 2;                 // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kGemmThreads = 192;                      // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr uint32_t kTmemCols = 512;                    // 2 accumulator buffers x 256 fp32 columns
+
+__device__ __forceinline__ uint32_t g_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void g_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void g_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void g_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4 (1024 B
+//   between 8-row groups) | [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N = 256, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+sqerr_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dw,
+                  int n_s, int m_tiles, int n_tiles, int k_blocks, double* __restrict__ err) {
+  extern __shared__ uint8_t gsm_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t raw = g_smem_u32(gsm_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gsm = gsm_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + kGStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kGStages + 4);
+  const uint32_t full0 = g_smem_u32(bars), empty0 = full0 + 8 * kGStages;
+  const uint32_t tfull0 = empty0 + 8 * kGStages, tempty0 = tfull0 + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = n_s * n_tiles * m_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGStages; ++s) {
+      g_mbar_init(full0 + 8 * s, 1);
+      g_mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      g_mbar_init(tfull0 + 8 * a, 1);
+      g_mbar_init(tempty0 + 8 * a, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // one warp owns the TMEM allocation (and the deallocation at the end)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, ph = 1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % m_tiles;
+        const int rest = tile / m_tiles;
+        const int nt = rest % n_tiles;
+        const int a = rest / n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          g_mbar_wait(empty0 + 8 * stage, ph);
+          g_mbar_expect_tx(full0 + 8 * stage, kStageBytes);
+          const uint32_t sa = base + stage * kStageBytes;
+          tma_load_2d(sa, &map_x, kb * kBK, mt * kBM, full0 + 8 * stage);
+          tma_load_3d(sa + kABytes, &map_dw, kb * kBK, nt * kBN, a, full0 + 8 * stage);
+          if (++stage == kGStages) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    uint32_t stage = 0, ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ab = (uint32_t)it & 1u;                  // accumulator buffer
+      const uint32_t aph = ((uint32_t)it >> 1) & 1u;
+      g_mbar_wait(tempty0 + 8 * ab, aph ^ 1u);                // epilogue has drained this buffer
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * kBN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        g_mbar_wait(full0 + 8 * stage, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + stage * kStageBytes;
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)                  // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, (kb | k) ? 1u : 0u);
+          umma_commit(empty0 + 8 * stage);                    // smem slot free once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(tfull0 + 8 * ab);   // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == kGStages) { stage = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: sum of squares of the accumulator =====================
+    const uint32_t quarter = (uint32_t)warp & 3u;              // TMEM lanes [32q, 32q+32) for this warp
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int a = (tile / m_tiles) / n_tiles;
+      const uint32_t ab = (uint32_t)it & 1u;
+      const uint32_t aph = ((uint32_t)it >> 1) & 1u;
+      g_mbar_wait(tfull0 + 8 * ab, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ab * kBN + ((quarter * 32u) << 16);
+      float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < kBN; c += 64) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr + c, v0);
+        tmem_ld32(taddr + c + 32, v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float f0 = __uint_as_float(v0[j]), f1 = __uint_as_float(v1[j]);
+          acc0 = __fmaf_rn(f0, f0, acc0);
+          acc1 = __fmaf_rn(f1, f1, acc1);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) g_mbar_arrive(tempty0 + 8 * ab);          // buffer may be overwritten by the next tile
+      double d = (double)acc0 + (double)acc1;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+      if (lane == 0) atomicAdd(err + a, d);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (no libcuda link dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+}  // namespace awqk
+
+using namespace awqk;
+
+extern "C" int awqk_abs_colsum(const void* x, int dtype, int64_t T, int64_t K, double* colsum, void* stream) {
+  if (!x || !colsum || T <= 0 || K <= 0) return AWQK_E_BADARG;
+  DeviceGuard guard(x);
+  if (guard.status != AWQK_OK) return guard.status;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rows_per_cta = 64;
+  dim3 grid((unsigned)ceil_div(K, 256), (unsigned)ceil_div(T, rows_per_cta));
+  if (dtype == AWQK_BF16)
+    abs_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), T, K, rows_per_cta, colsum);
+  else if (dtype == AWQK_FP16)
+    abs_colsum_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), T, K, rows_per_cta, colsum);
+  else if (dtype == AWQK_FP32)
+    abs_colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), T, K, rows_per_cta, colsum);
+  else
+    return AWQK_E_UNSUPPORTED;
+  AWQK_CUDA(cudaGetLastError());
+  return AWQK_OK;
+}
+
+extern "C" int awqk_alpha_grid(const double* colsum, int64_t T, int64_t K, int n_grid, float* s_grid,
+                               float* workspace_2n, void* stream) {
+  if (!colsum || !s_grid || !workspace_2n || T <= 0 || K <= 0 || n_grid <= 0 || n_grid > 256) return AWQK_E_BADARG;
+  DeviceGuard guard(colsum);
+  if (guard.status != AWQK_OK) return guard.status;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  unsigned int* mnmx = reinterpret_cast<unsigned int*>(workspace_2n);
+  alpha_grid_init<<<1, 256, 0, st>>>(n_grid, mnmx);
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(K, 256), 64), (unsigned)n_grid);
+  alpha_grid_raw<<<grid, 256, 0, st>>>(colsum, T, K, n_grid, s_grid, mnmx);
+  alpha_grid_norm<<<grid, 256, 0, st>>>(K, n_grid, s_grid, mnmx);
+  AWQK_CUDA(cudaGetLastError());
+  return AWQK_OK;
+}
+
+template <typename T>
+static int launch_delta(const T* w, int64_t n, int64_t K, int g, int bits, bool sym, const float* s, int n_s,
+                        __nv_bfloat16* dw, cudaStream_t st) {
+  const int64_t ctas = ceil_div(n, 256 * 8);
+  if (ctas > 0x7FFFFFFFLL) return AWQK_E_BADARG;
+#define AWQK_DELTA(GG, BB) fakequant_delta_kernel<T, GG, BB><<<(unsigned)ctas, 256, 0, st>>>(w, n, K, sym, s, n_s, dw)
+  if (bits == 4) {
+    if (g == 32) AWQK_DELTA(32, 4); else if (g == 64) AWQK_DELTA(64, 4); else AWQK_DELTA(128, 4);
+  } else {
+    if (g == 32) AWQK_DELTA(32, 8); else if (g == 64) AWQK_DELTA(64, 8); else AWQK_DELTA(128, 8);
+  }
+#undef AWQK_DELTA
+  AWQK_CUDA(cudaGetLastError());
+  return AWQK_OK;
+}
+
+extern "C" int awqk_fakequant_delta(const void* w, int dtype, int64_t C, int64_t K, int group_size, int bits,
+                                    int symmetric, const float* s, int n_s, void* dw_bf16, void* stream) {
+  if (!w || !s || !dw_bf16 || C <= 0 || K <= 0 || n_s <= 0 || (bits != 4 && bits != 8)) return AWQK_E_BADARG;
+  if (!(group_size == 32 || group_size == 64 || group_size == 128) || (K % group_size) != 0) return AWQK_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(dw_bf16)) & 15u)
+    return AWQK_E_ALIGN;
+  DeviceGuard guard(w);
+  if (guard.status != AWQK_OK) return guard.status;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  auto out = reinterpret_cast<__nv_bfloat16*>(dw_bf16);
+  const bool sym = symmetric != 0;
+  if (dtype == AWQK_BF16)
+    return launch_delta(reinterpret_cast<const __nv_bfloat16*>(w), C * K, K, group_size, bits, sym, s, n_s, out, st);
+  if (dtype == AWQK_FP16)
+    return launch_delta(reinterpret_cast<const __half*>(w), C * K, K, group_size, bits, sym, s, n_s, out, st);
+  if (dtype == AWQK_FP32)
+    return launch_delta(reinterpret_cast<const float*>(w), C * K, K, group_size, bits, sym, s, n_s, out, st);
+  return AWQK_E_UNSUPPORTED;
+}
+
+extern "C" int awqk_sqerr_gemm(const void* x_bf16, const void* dw_bf16, int64_t T, int64_t C, int64_t K, int n_s,
+                               double* err, void* stream) {
+  if (!x_bf16 || !dw_bf16 || !err || T <= 0 || C <= 0 || K <= 0 || n_s <= 0) return AWQK_E_BADARG;
+  if ((K % 8) != 0) return AWQK_E_UNSUPPORTED;    // TMA needs 16-byte row pitch
+  if ((reinterpret_cast<uintptr_t>(x_bf16) | reinterpret_cast<uintptr_t>(dw_bf16)) & 15u) return AWQK_E_ALIGN;
+  if (T > 0x7FFFFFFF || C > 0x7FFFFFFF || K > 0x7FFFFFFF) return AWQK_E_BADARG;
+  DeviceGuard guard(x_bf16);
+  if (guard.status != AWQK_OK) return guard.status;
+  EncodeTiledFn encode = get_encode_fn();
+  if (encode == nullptr) return AWQK_E_NODEVICE;
+
+  CUtensorMap map_x, map_dw;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)T};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {kBK, kBM};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x_bf16), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return AWQK_E_BADARG;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)C, (cuuint64_t)n_s};
+    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)C * (cuuint64_t)K * 2};
+    const cuuint32_t box[3] = {kBK, kBN, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (encode(&map_dw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(dw_bf16), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return AWQK_E_BADARG;
+  }
+  const int m_tiles = (int)ceil_div(T, kBM), n_tiles = (int)ceil_div(C, kBN), k_blocks = (int)ceil_div(K, kBK);
+  const int64_t total = (int64_t)n_s * m_tiles * n_tiles;
+  if (total > 0x7FFFFFFF) return AWQK_E_BADARG;
+  int dev = 0, sms = 0;
+  AWQK_CUDA(cudaGetDevice(&dev));
+  AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = (size_t)kGStages * kStageBytes + 1024 + 256;
+  AWQK_CUDA(cudaFuncSetAttribute(sqerr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)std::min<int64_t>(total, sms);
+  sqerr_gemm_kernel<<<grid, kGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(map_x, map_dw, n_s, m_tiles,
+                                                                                         n_tiles, k_blocks, err);
+  AWQK_CUDA(cudaGetLastError());
+  return AWQK_OK;
+}

@@ -1,0 +1,146 @@
+"""GPU (B200): the activation-aware search kernels (K2) against the oracle's definition
+(oracle/awq_oracle.py::search_scales -- PARITY UNPINNED: the reference has no such code, the oracle
+composes the reference's pinned group quantizer).
+
+Tolerances (north star): chosen alpha exact and final qweight / qzeros bit-exact *given equal scales*
+(the GPU's s grid is injected into the oracle), error scores within 1e-3 relative."""
+import pytest
+import torch
+
+from oracle import awq_oracle as O
+from tests import datagen
+from tests.util import assert_quant_equal, assert_same
+
+pytestmark = pytest.mark.gpu
+
+
+def test_abs_colsum_exact(native_lib, cuda_device):
+    from awq_quantizer import _native as N
+    for dt in ("bf16", "fp16", "fp32"):
+        X = datagen.activations(300, 520, dt, 11)
+        xd = X.to(cuda_device)
+        cs = torch.zeros(520, dtype=torch.float64, device=cuda_device)
+        assert native_lib.awqk_abs_colsum(xd.data_ptr(), N.dtype_code(xd.dtype), 300, 520, cs.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        want = X.double().abs().sum(0)
+        assert torch.equal(cs.cpu(), want), dt                     # fp64 accumulation of fp16/bf16 data is exact
+        assert torch.equal((cs.cpu() / 300).float(), O.activation_mean(X))
+
+
+def test_alpha_grid_close_to_oracle(native_lib, cuda_device):
+    from awq_quantizer import _native as N
+    X = datagen.activations(256, 1024, "bf16", 5)
+    m = O.activation_mean(X)
+    cs = X.double().abs().sum(0).to(cuda_device)
+    n = 20
+    s = torch.empty((n, 1024), dtype=torch.float32, device=cuda_device)
+    ws = torch.empty(2 * n, dtype=torch.float32, device=cuda_device)
+    assert native_lib.awqk_alpha_grid(cs.data_ptr(), 256, 1024, n, s.data_ptr(), ws.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    s = s.cpu()
+    assert torch.equal(s[0], torch.ones(1024))                     # alpha = 0
+    for i in range(n):
+        want = O.alpha_scales(m, i / n)
+        assert torch.allclose(s[i], want, rtol=2e-6, atol=0), i    # powf ulps; everything else is exact
+        assert abs(float(s[i].max() * s[i].min()) - 1.0) < 1e-5    # normalisation: max * min == 1
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16", "fp32"])
+@pytest.mark.parametrize("sym", [False, True])
+@pytest.mark.parametrize("g", [32, 128])
+def test_fakequant_delta_bit_exact(native_lib, cuda_device, dt, sym, g):
+    from awq_quantizer import _native as N
+    C, K, n_s = 48, 512, 3
+    W = datagen.weights((C, K), dt, datagen.seed_of("fq", dt, sym, g))
+    W[1, :128] = 0.0
+    X = datagen.activations(64, K, "bf16", 8)
+    m = O.activation_mean(X)
+    s = torch.stack([O.alpha_scales(m, a) for a in (0.0, 0.35, 0.8)])
+    wd, sd = W.to(cuda_device), s.to(cuda_device)
+    dw = torch.empty((n_s, C, K), dtype=torch.bfloat16, device=cuda_device)
+    assert native_lib.awqk_fakequant_delta(wd.data_ptr(), N.dtype_code(wd.dtype), C, K, g, 4, int(sym), sd.data_ptr(),
+                                           n_s, dw.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    for i in range(n_s):
+        want = O.fake_quant_delta(W, s[i], 4, g, sym).to(torch.bfloat16)
+        assert_same(dw[i].cpu().view(torch.int16), want.view(torch.int16), f"dW[{i}]")
+
+
+@pytest.mark.parametrize("T,C,K,n_s", [(128, 256, 64, 1), (256, 512, 256, 3), (200, 300, 320, 2), (512, 1024, 1024, 5),
+                                       (130, 260, 72, 1)])
+def test_sqerr_gemm_vs_fp64(native_lib, cuda_device, T, C, K, n_s):
+    """the tcgen05 GEMM + fused sum-of-squares epilogue on arbitrary bf16 operands (incl. tiles that run
+    past T, C and K: TMA zero fill)"""
+    g = torch.Generator().manual_seed(T * 7 + C)
+    X = (torch.randn((T, K), generator=g)).to(torch.bfloat16)
+    D = (torch.randn((n_s, C, K), generator=g) * 0.01).to(torch.bfloat16)
+    xd, dd = X.to(cuda_device), D.to(cuda_device)
+    err = torch.zeros(n_s, dtype=torch.float64, device=cuda_device)
+    assert native_lib.awqk_sqerr_gemm(xd.data_ptr(), dd.data_ptr(), T, C, K, n_s, err.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    for i in range(n_s):
+        want = float(((X.double() @ D[i].double().T) ** 2).sum())
+        got = float(err[i])
+        assert abs(got - want) <= 1e-5 * want, (i, got, want)
+    # accumulating call: err += ...
+    assert native_lib.awqk_sqerr_gemm(xd.data_ptr(), dd.data_ptr(), T, C, K, n_s, err.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    want0 = float(((X.double() @ D[0].double().T) ** 2).sum())
+    assert abs(float(err[0]) - 2 * want0) <= 2e-5 * want0
+
+
+def test_sqerr_gemm_persistent_many_tiles(native_lib, cuda_device):
+    """more tiles than SMs and many k-blocks: exercises ring wrap-around and both TMEM buffers"""
+    T, C, K, n_s = 1024, 2048, 2048, 6
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    X = torch.randn((T, K), generator=g, device=cuda_device).to(torch.bfloat16)
+    D = (torch.randn((n_s, C, K), generator=g, device=cuda_device) * 0.01).to(torch.bfloat16)
+    err = torch.zeros(n_s, dtype=torch.float64, device=cuda_device)
+    assert native_lib.awqk_sqerr_gemm(X.data_ptr(), D.data_ptr(), T, C, K, n_s, err.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    for i in range(n_s):
+        want = float(((X.double() @ D[i].double().T) ** 2).sum())   # fp64 matmul on the GPU (checker only)
+        assert abs(float(err[i]) - want) <= 1e-5 * want, (i, float(err[i]), want)
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_full_search_vs_oracle(native_lib, cuda_device, sym):
+    from awq_quantizer.quantization import AWQQuantizer
+    C, K, T, n = 256, 512, 192, 20
+    W = datagen.weights((C, K), "bf16", 21)
+    X = datagen.activations(T, K, "bf16", 22)
+    qz = AWQQuantizer(bits=4, group_size=128, symmetric=sym, device="cuda:0", logger_level="ERROR", n_grid=n)
+    got = qz.quantize(W, activations=X, pack=True)
+    # the GPU's scale grid is recomputed here and injected into the oracle ("given equal scales")
+    from awq_quantizer.quantization.search import search_device
+    r = search_device(W.to(cuda_device), X.to(cuda_device), bits=4, group_size=128, symmetric=sym, n_grid=n)
+    s_grid = r["s_grid"].cpu()
+    want = O.search_scales(W, X, 4, 128, sym, n_grid=n, s_grid=s_grid)
+    err = got["search_err"]
+    for i in range(n):
+        assert abs(float(err[i]) - want["err"][i]) <= 1e-3 * want["err"][i], (i, float(err[i]), want["err"][i])
+    srt = sorted(want["err"])
+    near_tie = (srt[1] - srt[0]) < 1e-3 * srt[0]
+    if not near_tie:                                              # near-ties are reported, not failed
+        assert int(got["best_idx"]) == want["best_idx"]
+        assert abs(float(got["alpha"]) - want["alpha"]) < 1e-7
+    assert int(got["best_idx"]) > 0                               # activation-aware scaling beats alpha = 0 here
+    s_best = got["awq_scale"]
+    assert torch.equal(s_best, s_grid[int(got["best_idx"])])
+    final = O.pack_result(O.quantize_scaled(W, s_best, 4, 128, sym))
+    assert_quant_equal(got, final, "final", keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
+    # scales from the oracle's own s (CPU pow) stay within 1 fp16 ulp
+    own = O.quantize_scaled(W, want["s_grid"][int(got["best_idx"])], 4, 128, sym)
+    a, b = got["scales"].view(torch.int16).int(), own["scales"].view(torch.int16).int()
+    assert int((a - b).abs().max()) <= 1
+
+
+def test_search_argument_errors(native_lib, cuda_device):
+    from awq_quantizer.quantization import AWQQuantizer
+    qz = AWQQuantizer(bits=4, group_size=128, symmetric=False, device="cuda:0", logger_level="ERROR")
+    W = datagen.weights((64, 256), "bf16", 1)
+    with pytest.raises(ValueError):
+        qz.quantize(W, activations=torch.zeros(16, 128, dtype=torch.bfloat16))     # wrong K
+    with pytest.raises(ValueError):
+        qz.quantize(W.reshape(64, 2, 128), activations=torch.zeros(16, 256, dtype=torch.bfloat16))  # not 2-D
+    assert native_lib.awqk_sqerr_gemm(None, None, 1, 1, 8, 1, None, None) == -1
