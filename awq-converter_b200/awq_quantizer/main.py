@@ -1,0 +1,316 @@
+"""``awq_quantizer`` CLI -- same flags, exit codes and output layout as the reference's main.py, re-hosted
+on the B200 path:
+
+* every flag of main.py:32-157 is accepted unchanged; additive flags: ``--pack`` (int32-packed
+  qweight/qzeros next to or instead of the unpacked codes), ``--arith {native,fp32}``, ``--config``
+  (the YAML file the reference documents but never wired, main.py:16 / USAGE.md:13-22);
+* tensor selection = main.py:243-253 (non-float / empty / numel < 128 are skipped, largest first);
+* ``--multi_gpu`` no longer repeats the whole model on every device (main.py:596-606): tensors are
+  partitioned largest-first onto the least-loaded device -- the reference's own, never-called,
+  partition_tensors (main.py:395-427) -- and under ``torchrun`` each rank quantizes only its shard and
+  writes its own chunk files; rank 0 gathers the chunk maps (NCCL/gloo all_gather_object) into
+  metadata.json;
+* ``--save_safetensors`` works (the reference hands nested dicts to save_file, main.py:478-490, and
+  fails): flat keys ``{name}.q / .scales / .zero_points / .bits / .group_size / .symmetric`` as in
+  test_quantization.py:182-189 (+ ``.qweight`` / ``.qzeros`` with --pack);
+* no CPU execution: ``--device cpu`` (or no visible GPU) ends with exit code 1 and a clear message.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import time
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import parallel
+from .model_loading import load_model_from_hub
+from .model_shapes import partition_lpt
+from .quantization.awq import AWQQuantizer
+from .utils.config import load_config
+from .utils.logger import get_logger
+
+
+def parse_args(argv=None) -> argparse.Namespace:
+    p = argparse.ArgumentParser(description="AWQ Quantizer CLI")
+    p.add_argument("--model_id", type=str, required=True, help="Model ID on HuggingFace Hub or path to local model")
+    p.add_argument("--output_dir", type=str, required=True, help="Directory to save quantized model")
+    p.add_argument("--bits", type=int, default=4, choices=[4, 8], help="Number of bits for quantization")
+    p.add_argument("--group_size", type=int, default=128, help="Group size for quantization")
+    p.add_argument("--symmetric", action="store_true", help="Use symmetric quantization")
+    p.add_argument("--zero_point", type=str, default="minmax", choices=["none", "minmax", "percentile"],
+                   help="Zero point calibration method")
+    p.add_argument("--percentile", type=float, default=0.99, help="Percentile for zero point calibration")
+    p.add_argument("--scale_method", type=str, default="mse", choices=["minmax", "mse"], help="Scale calibration method")
+    p.add_argument("--per_channel", action="store_true", help="Use per-channel quantization")
+    p.add_argument("--device", type=str, default="cuda" if torch.cuda.is_available() else "cpu",
+                   help="Device to use for quantization (cuda, cuda:0, cuda:1, cpu, or 'all' for all GPUs)")
+    p.add_argument("--num_workers", type=int, default=4, help="Number of worker threads for parallel processing per GPU")
+    p.add_argument("--max_memory", type=float, default=0.8, help="Maximum fraction of GPU memory to use (0.0-1.0)")
+    p.add_argument("--multi_gpu", action="store_true", help="Use all available GPUs for processing (overrides --device)")
+    p.add_argument("--batch_size", type=int, default=10, help="Number of tensors to process in each batch")
+    p.add_argument("--prefetch_factor", type=int, default=2, help="Number of batches to prefetch")
+    p.add_argument("--memory_efficient", action="store_true", help="Enable memory-efficient mode")
+    p.add_argument("--log_level", type=str, default="INFO", choices=["DEBUG", "INFO", "WARNING", "ERROR", "CRITICAL"],
+                   help="Logging level")
+    p.add_argument("--log_file", type=str, help="Log file path")
+    p.add_argument("--save_safetensors", action="store_true", help="Save in safetensors format instead of pytorch format")
+    p.add_argument("--chunk_size", type=int, default=10, help="Number of tensors to save in each chunk (for large models)")
+    # additive
+    p.add_argument("--pack", action="store_true", help="emit int32-packed qweight/qzeros (8 nibbles per word)")
+    p.add_argument("--arith", type=str, default="native", choices=["native", "fp32"],
+                   help="arithmetic contract: native = the reference's own (input dtype), fp32 = reference on w.float()")
+    p.add_argument("--config", type=str, help="YAML config (reference schema); CLI flags win over it")
+    return p.parse_args(argv)
+
+
+def get_available_gpus(logger=None) -> List[str]:
+    if not torch.cuda.is_available():
+        if logger:
+            logger.warning("No CUDA devices available")
+        return []
+    out = []
+    for i in range(torch.cuda.device_count()):
+        if logger:
+            logger.info(f"Found CUDA device {i}: {torch.cuda.get_device_name(i)}")
+        out.append(f"cuda:{i}")
+    return out
+
+
+def get_device_memory_info(device_idx: int) -> Tuple[float, float]:
+    if not torch.cuda.is_available():
+        return 0.0, 0.0
+    try:
+        free, total = torch.cuda.mem_get_info(device_idx)
+        return total / 1024 ** 3, free / 1024 ** 3
+    except Exception:
+        return 0.0, 0.0
+
+
+def prepare_tensors_for_quantization(tensors: Dict[str, torch.Tensor], device: str, max_memory_fraction: float = 0.8,
+                                     batch_size: int = 10, logger=None) -> List[Dict[str, torch.Tensor]]:
+    """main.py:216-330: skip rules, largest-first order, batches of <= batch_size tensors that fit the
+    GPU-memory budget.  Tensors stay on the host; the quantizer uploads them (pipelined)."""
+    items = []
+    for name, t in tensors.items():
+        if not isinstance(t, torch.Tensor) or not t.is_floating_point() or t.numel() == 0:
+            if logger:
+                logger.warning(f"Skipping invalid tensor: {name}")
+            continue
+        if t.numel() < 128:
+            if logger:
+                logger.warning(f"Skipping tensor too small for grouping: {name}")
+            continue
+        items.append((name, t, t.numel() * t.element_size()))
+    items.sort(key=lambda x: x[2], reverse=True)
+    budget = None
+    if device.startswith("cuda") and torch.cuda.is_available():
+        idx = int(device.split(":")[1]) if ":" in device else torch.cuda.current_device()
+        total = torch.cuda.get_device_properties(idx).total_memory
+        budget = int(total * max_memory_fraction) - torch.cuda.memory_allocated(idx)
+    batches, cur, cur_bytes = [], {}, 0
+    for name, t, nbytes in items:
+        # x3: input + int32 codes + slack -- a batch must fit on the device at once
+        if cur and (len(cur) >= batch_size or (budget is not None and cur_bytes + 3 * nbytes > budget)):
+            batches.append(cur)
+            cur, cur_bytes = {}, 0
+        cur[name] = t
+        cur_bytes += 3 * nbytes
+    if cur:
+        batches.append(cur)
+    if logger:
+        logger.info(f"Created {len(batches)} batches with {sum(len(b) for b in batches)} total tensors")
+    return batches
+
+
+def quantize_tensor_batch(tensor_items: List[tuple], quantizer: AWQQuantizer, device: str, logger=None,
+                          pack: bool = False) -> Dict[str, dict]:
+    """main.py:333-392 (without its OOM -> CPU fallback: failures are logged and the tensor is skipped)."""
+    out = {}
+    for name, tensor in tensor_items:
+        if logger:
+            logger.info(f"Quantizing tensor: {name} on {device}")
+        try:
+            out[name] = quantizer.quantize(tensor, pack=pack)
+            if logger:
+                logger.info(f"Successfully quantized tensor: {name} on {device}")
+        except Exception as e:
+            if logger:
+                logger.error(f"Failed to quantize tensor {name} on {device}: {e}")
+    return out
+
+
+def partition_tensors(tensors: Dict[str, torch.Tensor], num_partitions: int) -> List[Dict[str, torch.Tensor]]:
+    """main.py:395-427 -- largest first onto the least-loaded partition, by bytes."""
+    if num_partitions <= 1:
+        return [tensors]
+    bins = partition_lpt([(n, t.numel() * t.element_size()) for n, t in tensors.items()], num_partitions)
+    return [{n: tensors[n] for n in b} for b in bins]
+
+
+def _flatten_for_safetensors(chunk: Dict[str, dict]) -> Dict[str, torch.Tensor]:
+    rename = {"tensor_q": "q"}
+    flat = {}
+    for name, qd in chunk.items():
+        for k, v in qd.items():
+            if isinstance(v, torch.Tensor):
+                flat[f"{name}.{rename.get(k, k)}"] = v.contiguous() if v.dim() else v.reshape(1)
+    return flat
+
+
+def save_model_in_chunks(tensors: Dict[str, dict], output_dir: str, chunk_size: int = 10, use_safetensors: bool = False,
+                         logger=None, rank: int = 0, world: int = 1, write_metadata: bool = True) -> dict:
+    """main.py:430-512.  Chunk files ``model_chunk_%04d`` (+ ``rankN_`` prefix when sharded over ranks)."""
+    os.makedirs(output_dir, exist_ok=True)
+    names = list(tensors.keys())
+    num_chunks = (len(names) + chunk_size - 1) // chunk_size
+    prefix = f"rank{rank}_" if world > 1 else ""
+    example = tensors[names[0]] if names else {}
+    params = {k: (example[k].item() if k in example else None) for k in ("bits", "group_size", "symmetric")}
+    tensor_to_chunk, files = {}, []
+    for c in range(num_chunks):
+        part = {n: tensors[n] for n in names[c * chunk_size:(c + 1) * chunk_size]}
+        for n in part:
+            tensor_to_chunk[n] = c
+        base = os.path.join(output_dir, f"{prefix}model_chunk_{c:04d}")
+        if use_safetensors:
+            from safetensors.torch import save_file
+            save_file(_flatten_for_safetensors(part), base + ".safetensors")
+            files.append(os.path.basename(base) + ".safetensors")
+        else:
+            torch.save(part, base + ".pt")
+            files.append(os.path.basename(base) + ".pt")
+        if logger:
+            logger.info(f"Saved chunk {c + 1}/{num_chunks} with {len(part)} tensors")
+    meta = {"rank": rank, "num_chunks": num_chunks, "chunk_size": chunk_size, "tensor_to_chunk": tensor_to_chunk,
+            "format": "safetensors" if use_safetensors else "pytorch", "num_tensors": len(names),
+            "quantization_params": params, "files": files}
+    if write_metadata and world == 1:
+        with open(os.path.join(output_dir, "metadata.json"), "w") as f:
+            json.dump({k: v for k, v in meta.items() if k != "rank"}, f, indent=2)
+    return meta
+
+
+def _apply_config(args: argparse.Namespace, argv) -> None:
+    if not args.config:
+        return
+    cfg = load_config(args.config)
+    given = {a.split("=")[0].lstrip("-") for a in (argv or []) if a.startswith("--")}
+    for key in ("bits", "group_size", "symmetric", "zero_point", "percentile", "scale_method", "per_channel"):
+        if key not in given and cfg.get(f"quantization.{key}") is not None:
+            setattr(args, key, cfg.get(f"quantization.{key}"))
+    args.skip_layers = list(cfg.get("quantization.skip_layers", []) or [])
+
+
+def main(argv=None) -> int:
+    logger = None
+    try:
+        import sys
+        argv = sys.argv[1:] if argv is None else list(argv)
+        args = parse_args(argv)
+        args.skip_layers = []
+        _apply_config(args, argv)
+        logger = get_logger(name="awq_quantizer", level=args.log_level, to_file=args.log_file is not None,
+                            file_path=args.log_file)
+        os.makedirs(args.output_dir, exist_ok=True)
+        rank, world = parallel.init_distributed()
+        local = parallel.rank_info()[2]
+
+        if world > 1:
+            devices = [f"cuda:{local}"]
+        elif args.multi_gpu or args.device.lower() == "all":
+            devices = get_available_gpus(logger)
+        else:
+            devices = [args.device]
+        if not devices or any(not d.startswith("cuda") for d in devices) or not torch.cuda.is_available():
+            logger.error("This build of awq_quantizer runs on CUDA (B200) only; no CPU execution path exists "
+                         f"(requested devices: {devices or 'none found'})")
+            return 1
+        for d in devices:
+            idx = int(d.split(":")[1]) if ":" in d else torch.cuda.current_device()
+            tot, free = get_device_memory_info(idx)
+            logger.info(f"Using GPU {d}: {torch.cuda.get_device_name(idx)} ({tot:.1f} GB total, {free:.1f} GB free)")
+
+        logger.info(f"Loading model from {args.model_id}")
+        try:
+            tensors = load_model_from_hub(args.model_id, logger_level=args.log_level).load_tensors()
+        except Exception as e:
+            logger.error(f"Failed to load model: {e}")
+            return 1
+        if args.skip_layers:
+            tensors = {n: t for n, t in tensors.items() if not any(s in n for s in args.skip_layers)}
+
+        start = time.time()
+        quantizable = {n: t for b in prepare_tensors_for_quantization(tensors, devices[0], args.max_memory, 1 << 30, None)
+                       for n, t in b.items()}
+        if world > 1:                                    # rank-local shard (torchrun)
+            mine = set(parallel.shard_for_rank(parallel.tensor_costs(quantizable), world, rank))
+            shards = [{n: t for n, t in quantizable.items() if n in mine}]
+        else:                                            # one process, 1..N devices
+            shards = partition_tensors(quantizable, len(devices))
+
+        def run_device(device: str, shard: Dict[str, torch.Tensor]) -> Dict[str, dict]:
+            qz = AWQQuantizer(bits=args.bits, group_size=args.group_size, symmetric=args.symmetric,
+                              zero_point=args.zero_point, percentile=args.percentile, scale_method=args.scale_method,
+                              per_channel=args.per_channel, device=device, logger_name=f"awq_quantizer_{device}",
+                              logger_level=args.log_level, logger_to_file=args.log_file is not None,
+                              logger_file_path=args.log_file, arith=args.arith)
+            done: Dict[str, dict] = {}
+            batches = prepare_tensors_for_quantization(shard, device, args.max_memory, args.batch_size, logger)
+            with ThreadPoolExecutor(max_workers=max(1, args.num_workers)) as ex:
+                futs = [ex.submit(quantize_tensor_batch, list(b.items()), qz, device, logger, args.pack) for b in batches]
+                for i, fut in enumerate(futs):
+                    try:
+                        done.update(fut.result())
+                        logger.info(f"Completed batch {i + 1}/{len(batches)} on {device}")
+                    except Exception as e:
+                        logger.error(f"Error processing batch {i} on {device}: {e}")
+            return done
+
+        quantized: Dict[str, dict] = {}
+        if len(devices) == 1:
+            quantized = run_device(devices[0], shards[0])
+        else:
+            with ThreadPoolExecutor(max_workers=len(devices)) as ex:
+                for part in ex.map(lambda ds: run_device(*ds), zip(devices, shards)):
+                    quantized.update(part)
+
+        if world == 1 and not quantized:
+            logger.error("No tensors were successfully quantized")
+            return 1
+        logger.info(f"Successfully quantized {len(quantized)} tensors")
+        try:
+            meta = save_model_in_chunks(quantized, args.output_dir, args.chunk_size, args.save_safetensors, logger,
+                                        rank=rank, world=world)
+        except Exception as e:
+            logger.error(f"Failed to save quantized model: {e}")
+            return 1
+        if world > 1:
+            metas = parallel.gather_metadata(meta)
+            if rank == 0:
+                merged = parallel.merge_chunk_maps(metas)
+                merged.update({"chunk_size": args.chunk_size, "format": meta["format"], "world_size": world,
+                               "quantization_params": next((m["quantization_params"] for m in metas if m["num_tensors"]),
+                                                           meta["quantization_params"])})
+                with open(os.path.join(args.output_dir, "metadata.json"), "w") as f:
+                    json.dump(merged, f, indent=2)
+                if not merged["num_tensors"]:
+                    logger.error("No tensors were successfully quantized")
+                    return 1
+        logger.info(f"Quantization complete in {time.time() - start:.2f} seconds")
+        return 0
+    except SystemExit:
+        raise
+    except Exception as e:
+        if logger is not None:
+            logger.error(f"Error during quantization: {e}")
+        else:
+            print(f"Error during quantization: {e}")
+        return 1
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

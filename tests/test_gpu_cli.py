@@ -1,0 +1,70 @@
+"""GPU: the CLI end to end on a tiny local model directory (the reference's offline path:
+--model_id <dir>), .pt and safetensors outputs, against the oracle."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import awq_oracle as O
+from tests import datagen
+from tests.util import assert_quant_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def make_model(tmp_path):
+    from safetensors.torch import save_file
+    t = {"layers.0.fc1.weight": datagen.weights((64, 256), "bf16", 1), "layers.0.fc1.bias": datagen.weights((256,), "bf16", 2),
+         "layers.0.fc2.weight": datagen.weights((32, 512), "bf16", 3), "norm.weight": datagen.weights((100,), "bf16", 4),
+         "ragged.weight": datagen.weights((6, 200), "fp32", 5), "position_ids": torch.arange(16)}
+    d = tmp_path / "model"
+    d.mkdir()
+    save_file({k: v for k, v in list(t.items())[:3]}, str(d / "model-00001-of-00002.safetensors"))
+    save_file({k: v for k, v in list(t.items())[3:]}, str(d / "model-00002-of-00002.safetensors"))
+    return str(d), t
+
+
+def test_cli_pt_output_matches_reference_layout(native_lib, cuda_device, tmp_path):
+    from awq_quantizer import main as cli
+    model, tensors = make_model(tmp_path)
+    out = str(tmp_path / "out")
+    rc = cli.main(["--model_id", model, "--output_dir", out, "--device", "cuda:0", "--chunk_size", "2",
+                   "--log_level", "ERROR", "--num_workers", "2"])
+    assert rc == 0
+    md = json.load(open(os.path.join(out, "metadata.json")))
+    expect = ["layers.0.fc1.weight", "layers.0.fc1.bias", "layers.0.fc2.weight", "ragged.weight"]   # numel >= 128, float
+    assert sorted(md["tensor_to_chunk"]) == sorted(expect) and md["num_chunks"] == 2 and md["format"] == "pytorch"
+    assert md["quantization_params"] == {"bits": 4, "group_size": 128, "symmetric": False}        # CLI default: asymmetric
+    got = {}
+    for c in range(md["num_chunks"]):
+        got.update(torch.load(os.path.join(out, f"model_chunk_{c:04d}.pt")))
+    for n in expect:
+        assert_quant_equal(got[n], O.group_quant_vec(tensors[n], 4, 128, False, False), n)   # CLI default per_channel=False
+
+
+def test_cli_safetensors_packed_symmetric(native_lib, cuda_device, tmp_path):
+    from safetensors.torch import load_file
+    from awq_quantizer import main as cli
+    model, tensors = make_model(tmp_path)
+    out = str(tmp_path / "out_st")
+    rc = cli.main(["--model_id", model, "--output_dir", out, "--device", "cuda:0", "--save_safetensors", "--pack",
+                   "--symmetric", "--per_channel", "--log_level", "ERROR"])
+    assert rc == 0                                              # the reference returns 1 here (nested dicts, main.py:478-490)
+    flat = load_file(os.path.join(out, "model_chunk_0000.safetensors"))
+    for n in ("layers.0.fc1.weight", "layers.0.fc2.weight", "ragged.weight"):
+        want = O.pack_result(O.group_quant_vec(tensors[n], 4, 128, True, True))
+        assert torch.equal(flat[n + ".q"], want["tensor_q"]) and torch.equal(flat[n + ".qweight"], want["qweight"])
+        assert torch.equal(flat[n + ".scales"].view(torch.int16), want["scales"].view(torch.int16))
+        assert torch.equal(flat[n + ".zero_points"], want["zero_points"]) and torch.equal(flat[n + ".qzeros"], want["qzeros"])
+        assert int(flat[n + ".bits"]) == 4 and int(flat[n + ".group_size"]) == 128 and bool(flat[n + ".symmetric"])
+
+
+def test_cli_multi_gpu_flag_partitions_instead_of_repeating(native_lib, cuda_device, tmp_path):
+    from awq_quantizer import main as cli
+    model, tensors = make_model(tmp_path)
+    out = str(tmp_path / "out_mg")
+    rc = cli.main(["--model_id", model, "--output_dir", out, "--multi_gpu", "--log_level", "ERROR"])
+    assert rc == 0
+    md = json.load(open(os.path.join(out, "metadata.json")))
+    assert md["num_tensors"] == 4

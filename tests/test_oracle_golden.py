@@ -153,3 +153,34 @@ def test_search_oracle_prefers_activation_aware_scaling():
     dW = O.fake_quant_delta(W, torch.ones(256), 4, 128, False).double()
     ref = float(((X.double() @ dW.T) ** 2).mean())
     assert abs(ref - r["err"][0]) <= 1e-12 * max(1.0, ref)
+
+
+def test_c_oracle_matches_goldens_and_python_oracle(small, special):
+    """the plain-C restatement (oracle/awq_oracle.c, also the fast CPU baseline) against the same
+    reference fixtures"""
+    from oracle import c_oracle as CO
+    n = 0
+    for c in cases.small_cases():
+        if c["dtype"] == "fp64":
+            continue
+        w = cases.case_input(c)
+        if w.numel() < c["group_size"]:
+            continue                                        # bypass layouts are host logic, not in the C core
+        key = cases.case_key(c)
+        got = CO.group_quant(w, c["bits"], c["group_size"], c["symmetric"], threads=2)
+        want = golden_result(small, key)
+        assert_quant_equal(got, {k: v.reshape(got[k].shape) for k, v in want.items()}, key)
+        n += 1
+    assert n > 300
+    for name, master in cases.special_inputs().items():
+        for dt in ("bf16", "fp16", "fp32"):
+            w = master.to(datagen.DTYPES[dt])
+            for sym in (False, True):
+                key = f"{name}_{dt}_{'sym' if sym else 'asym'}"
+                got = CO.group_quant(w, 4, 128, sym, threads=2)
+                assert_quant_equal(got, golden_result(special, key), key)
+                assert_same(CO.dequant(got), torch.from_numpy(special[key + "/dequant"]), key + "/dequant")
+                assert_quant_equal(CO.group_quant(w, 4, 128, sym, arith="fp32", threads=2),
+                                   O.group_quant_vec(w, 4, 128, sym, True, arith="fp32"), key + "/fp32")
+    codes = torch.randint(0, 16, (7, 100), dtype=torch.int32)
+    assert torch.equal(CO.pack_rows(codes, 0, 4), O.pack_rows_u32(codes, 0, 4))
