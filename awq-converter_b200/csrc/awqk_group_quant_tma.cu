@@ -114,46 +114,49 @@ template <int QMIN>
 struct PairQuant<AR_F32, QMIN> {
   // v = q + zp (fp32), t = v + 1.5*2^23 -> low 16 bits of each t hold round(v) as an s16
   // (|v| < 2^14 guaranteed by the fast-group predicate)
+  // the magic constant carries -QMIN, so the low half IS the unsigned code before clamping
+  // (adding an integer to the magic does not move rounding ties: 1.5*2^23 - QMIN stays even-aligned)
   float2 zp2, magic2;
-  __device__ __forceinline__ void init(float zp) {
-    zp2 = make_float2(zp, zp);
-    magic2 = make_float2(12582912.0f, 12582912.0f);
-  }
+  __device__ __forceinline__ void prepare() { magic2 = make_float2(12582912.0f - (float)QMIN, 12582912.0f - (float)QMIN); }
+  __device__ __forceinline__ void init(float zp) { zp2 = make_float2(zp, zp); }
   __device__ __forceinline__ uint32_t run(float2 q) const {
     const float2 t = __fadd2_rn(__fadd2_rn(q, zp2), magic2);
     const uint32_t both = __byte_perm(__float_as_uint(t.x), __float_as_uint(t.y), 0x5410);
-    constexpr uint32_t REBASE = (uint32_t)((-QMIN) & 0xFFFF) * 0x00010001u;
-    return __viaddmin_s16x2_relu(both, REBASE, 0x000F000Fu);
+    return __vimin_s16x2_relu(both, 0x000F000Fu);
   }
 };
 template <int QMIN>
 struct PairQuant<AR_BF16, QMIN> {
   // a = bf16(q); b = bf16(a + zp); t = bf16(b + 192): [128,256) has ulp 1 -> bits = 0x4340 + round(b)
   __nv_bfloat162 zp2, magic2;
-  __device__ __forceinline__ void init(float zp) {
-    zp2 = __float2bfloat162_rn(zp);
+  uint32_t rebase;
+  __device__ __forceinline__ void prepare() {
     magic2 = __float2bfloat162_rn(192.0f);
+    rebase = (uint32_t)((-(0x4340 + QMIN)) & 0xFFFF) * 0x00010001u;
+    asm volatile("" : "+r"(rebase));                 // one live register, not one re-materialisation per use
   }
+  __device__ __forceinline__ void init(float zp) { zp2 = __float2bfloat162_rn(zp); }
   __device__ __forceinline__ uint32_t run(float2 q) const {
     const __nv_bfloat162 a = __float22bfloat162_rn(q);
     const __nv_bfloat162 t = __hadd2(__hadd2(a, zp2), magic2);
-    constexpr uint32_t REBASE = (uint32_t)((-(0x4340 + QMIN)) & 0xFFFF) * 0x00010001u;
-    return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), REBASE, 0x000F000Fu);
+    return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), rebase, 0x000F000Fu);
   }
 };
 template <int QMIN>
 struct PairQuant<AR_F16, QMIN> {
   // fp16: [1024,2048) has ulp 1 -> magic 1536 = 0x6600
   __half2 zp2, magic2;
-  __device__ __forceinline__ void init(float zp) {
-    zp2 = __float2half2_rn(zp);
+  uint32_t rebase;
+  __device__ __forceinline__ void prepare() {
     magic2 = __float2half2_rn(1536.0f);
+    rebase = (uint32_t)((-(0x6600 + QMIN)) & 0xFFFF) * 0x00010001u;
+    asm volatile("" : "+r"(rebase));
   }
+  __device__ __forceinline__ void init(float zp) { zp2 = __float2half2_rn(zp); }
   __device__ __forceinline__ uint32_t run(float2 q) const {
     const __half2 a = __float22half2_rn(q);
     const __half2 t = __hadd2(__hadd2(a, zp2), magic2);
-    constexpr uint32_t REBASE = (uint32_t)((-(0x6600 + QMIN)) & 0xFFFF) * 0x00010001u;
-    return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), REBASE, 0x000F000Fu);
+    return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), rebase, 0x000F000Fu);
   }
 };
 
@@ -214,12 +217,14 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   }
 
   // ================================ consumers =================================================
-  // per-thread invariants; everything that moves from tile to tile advances by a constant stride
+  // per-thread invariants.  Output addresses are (thread base) + it * (byte stride): one IMAD.WIDE
+  // per store, no loop-carried 64-bit pointers.
   const uint32_t thr_elem = (uint32_t)warp * kV2WarpTile + (uint32_t)lane * 32u;     // within the CTA tile
   const int64_t e_first = tile0 * kV2CtaTile + thr_elem;
   const int64_t e_stride = (int64_t)gridDim.x * kV2CtaTile;
-  // number of iterations in which this thread's 32 elements exist (whole groups are valid or not)
-  const int64_t valid_iters = (n_elems > e_first) ? (n_elems - e_first + e_stride - 1) / e_stride : 0;
+  const uint32_t iters = (uint32_t)n_iters;
+  // iterations in which this thread's 32 elements exist (whole groups are valid or not)
+  const uint32_t valid_iters = (n_elems > e_first) ? (uint32_t)((n_elems - e_first + e_stride - 1) / e_stride) : 0u;
   const int rot = (lane >> 1) & 3;
   const uint32_t smem_thr = smem_u32(smem) + (uint32_t)warp * (kV2WarpTile * 2) + (uint32_t)lane * 64u;
   uint32_t ld_off[4];
@@ -228,19 +233,24 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     ld_off[c] = smem_thr + (uint32_t)(((c + rot) & 3) << 4);
     asm volatile("" : "+r"(ld_off[c]));             // (no per-tile re-derivation from SR_CgaCtaId)
   }
-  uint32_t* q_ptr = out.q_packed + (e_first >> 3);
-  __half* s_ptr = out.scales + e_first / G;
-  int32_t* z_ptr = (out.zp != nullptr) ? out.zp + e_first / G : nullptr;
-  uint32_t* zq_ptr = (out.zp_packed != nullptr) ? out.zp_packed + e_first / (8 * G) : nullptr;
-  const int64_t q_stride = e_stride >> 3, g_stride = e_stride / G, zq_stride = e_stride / (8 * G);
+  uint8_t* const q_base = reinterpret_cast<uint8_t*>(out.q_packed + (e_first >> 3));
+  uint8_t* const s_base = reinterpret_cast<uint8_t*>(out.scales + e_first / G);
+  uint8_t* const z_base = reinterpret_cast<uint8_t*>(out.zp + e_first / G);
+  uint8_t* const zq_base = reinterpret_cast<uint8_t*>(out.zp_packed + e_first / (8 * G));
+  const uint32_t q_step = (uint32_t)(e_stride >> 3) * 4u;          // bytes per iteration (< 2^32: grid <= 3*SMs)
+  const uint32_t s_step = (uint32_t)(e_stride / G) * 2u;
+  const uint32_t z_step = (uint32_t)(e_stride / G) * 4u;
+  const uint32_t zq_step = (uint32_t)(e_stride / (8 * G)) * 4u;
+  const bool has_zp = out.zp != nullptr, has_zq = out.zp_packed != nullptr;
   const bool leader = (lane % LPG) == 0;
   const bool zq_writer = (lane % LPW) == 0;
   const uint32_t zq_shift = 4u * ((uint32_t)(lane / LPG) & 7u);
   const uint32_t zq_mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
 
   PairQuant<A, QMIN> pq;
+  pq.prepare();
   uint32_t stage = 0, ph = 0;
-  for (int64_t it = 0; it < n_iters; ++it) {
+  for (uint32_t it = 0; it < iters; ++it) {
     const bool valid = it < valid_iters;
     mbar_wait(full0 + 8 * stage, ph);
     // 64 B per thread as 4 x LDS.128.  Register slot c holds 16-byte chunk (c + rot) & 3 of the
@@ -327,26 +337,20 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
 
     // ---- stores ------------------------------------------------------------------------------
     const int zi = f2i_x86(zp);
-    if (valid) {
-      // slot c holds chunk (c + rot) & 3  ->  chunk k sits in slot (k - rot) & 3: rotate left by rot
-      uint32_t o0 = words[0], o1 = words[1], o2 = words[2], o3 = words[3];
-      if (rot & 1) { const uint32_t t = o3; o3 = o2; o2 = o1; o1 = o0; o0 = t; }
-      if (rot & 2) { uint32_t t = o0; o0 = o2; o2 = t; t = o1; o1 = o3; o3 = t; }
-      st_stream16(q_ptr, make_uint4(o0, o1, o2, o3));
-      if (leader) {
-        *s_ptr = __float2half_rn(sc);
-        if (z_ptr != nullptr) *z_ptr = zi;
-      }
+    // slot c holds chunk (c + rot) & 3  ->  chunk k sits in slot (k - rot) & 3: rotate left by rot
+    uint32_t o0 = words[0], o1 = words[1], o2 = words[2], o3 = words[3];
+    if (rot & 1) { const uint32_t t = o3; o3 = o2; o2 = o1; o1 = o0; o0 = t; }
+    if (rot & 2) { uint32_t t = o0; o0 = o2; o2 = t; t = o1; o1 = o3; o3 = t; }
+    if (valid) st_stream16(q_base + (uint64_t)it * q_step, make_uint4(o0, o1, o2, o3));
+    if (valid && leader) {
+      *reinterpret_cast<__half*>(s_base + (uint64_t)it * s_step) = __float2half_rn(sc);
+      if (has_zp) *reinterpret_cast<int32_t*>(z_base + (uint64_t)it * z_step) = zi;
     }
-    if (zq_ptr != nullptr) {
+    if (has_zq) {
       const uint32_t uz = (valid && leader && zi != INT32_MIN) ? ((uint32_t)(zi - QMIN) & 15u) : 0u;
       const uint32_t wordz = __reduce_or_sync(zq_mask, uz << zq_shift);
-      if (valid && zq_writer) *zq_ptr = wordz;
-      zq_ptr += zq_stride;
+      if (valid && zq_writer) *reinterpret_cast<uint32_t*>(zq_base + (uint64_t)it * zq_step) = wordz;
     }
-    q_ptr += q_stride;
-    s_ptr += g_stride;
-    if (z_ptr != nullptr) z_ptr += g_stride;
   }
 }
 
