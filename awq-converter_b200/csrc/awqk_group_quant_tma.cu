@@ -14,6 +14,8 @@
 //     magic-constant add, clamp + rebase in ONE integer instruction per pair (VIADDMNMX.S16x2.RELU),
 //     nibble merge by one IMAD per pair + 3 PRMT per word.
 // A warp tile is 1024 elements = 8/16/32 groups, i.e. a whole number of packed zero-point words.
+#include <atomic>
+
 #include "awqk_common.cuh"
 
 namespace awqk {
@@ -363,15 +365,20 @@ static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, cudaStrea
   const int64_t want = (int64_t)sms * 3;
   const unsigned grid = (unsigned)(n_tiles < want ? n_tiles : want);
   const size_t smem = (size_t)kV2Stages * kV2StageBytes + 2 * kV2Stages * sizeof(uint64_t);
+  // the dynamic-smem opt-in is per (kernel instantiation, device): set once, then immutable
+  static std::atomic<uint64_t> configured[2] = {{0}, {0}};
+  const uint64_t bit = 1ull << (dev & 63);
+  const bool need = !(configured[sym ? 1 : 0].load(std::memory_order_acquire) & bit);
   if (sym) {
     auto k = group_quant_tma<InT, A, G, true>;
-    AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
   } else {
     auto k = group_quant_tma<InT, A, G, false>;
-    AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
   }
+  if (need) configured[sym ? 1 : 0].fetch_or(bit, std::memory_order_release);
   AWQK_CUDA(cudaGetLastError());
   return AWQK_OK;
 }

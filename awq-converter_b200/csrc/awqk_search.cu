@@ -15,6 +15,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "awqk_common.cuh"
 
@@ -201,6 +202,142 @@ fakequant_delta_kernel(const T* __restrict__ w, int64_t n_elems, int64_t K, bool
       o[i / 2] = *reinterpret_cast<const uint32_t*>(&b);
     }
     if (valid) st_stream16(dw + (int64_t)a * n_elems + e0, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// ---- v2: 32 consecutive elements per thread (a group of 128 = 4 lanes), packed fp32x2 math,
+// reciprocals of the scale vectors precomputed (exact division by the hoisted-reciprocal sequence).
+// CTA = 8 rows x 1024 columns: the 8 warps read the same s / 1/s slab (L1 hits).
+__global__ void __launch_bounds__(256)
+rcp_grid_kernel(const float* __restrict__ s, int64_t n, float* __restrict__ r) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) r[i] = refined_rcp(s[i]);
+}
+
+template <typename T>
+__device__ __forceinline__ void load32(const T* p, float2 (&f)[16]);
+template <>
+__device__ __forceinline__ void load32<__nv_bfloat16>(const __nv_bfloat16* p, float2 (&f)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p) + c);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      f[4 * c + i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+  }
+}
+template <>
+__device__ __forceinline__ void load32<__half>(const __half* p, float2 (&f)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p) + c);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[4 * c + i] = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+  }
+}
+template <>
+__device__ __forceinline__ void load32<float>(const float* p, float2 (&f)[16]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(p) + c);
+    f[2 * c] = make_float2(r.x, r.y);
+    f[2 * c + 1] = make_float2(r.z, r.w);
+  }
+}
+
+template <typename T, int G, int BITS>
+__global__ void __launch_bounds__(256)
+fakequant_delta_v2(const T* __restrict__ w, int64_t C, int64_t K, bool sym, const float* __restrict__ s_grid,
+                   const float* __restrict__ r_grid, int n_s, __nv_bfloat16* __restrict__ dw) {
+  constexpr int LPG = G / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.y * 8 + warp;
+  const int64_t col = (int64_t)blockIdx.x * 1024 + lane * 32;
+  const bool valid = row < C && col < K;
+  const float qmin = sym ? -(float)(1 << (BITS - 1)) : 0.0f;
+  const float qmax = sym ? (float)((1 << (BITS - 1)) - 1) : (float)((1 << BITS) - 1);
+  const float2 magic2 = make_float2(12582912.0f, 12582912.0f), nmagic2 = make_float2(-12582912.0f, -12582912.0f);
+  float2 wv[16];
+  if (valid) load32<T>(w + row * K + col, wv);
+  else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wv[i] = make_float2(0.0f, 0.0f);
+  }
+  const int64_t cc = valid ? col : 0;
+  __nv_bfloat16* out = dw + row * K + col;
+  const int64_t plane = C * K;
+#pragma unroll 1
+  for (int a = 0; a < n_s; ++a) {
+    const float4* sp = reinterpret_cast<const float4*>(s_grid + (int64_t)a * K + cc);
+    const float4* rp = reinterpret_cast<const float4*>(r_grid + (int64_t)a * K + cc);
+    float2 sv[16], x[16];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 t = __ldg(sp + c);
+      sv[2 * c] = make_float2(t.x, t.y);
+      sv[2 * c + 1] = make_float2(t.z, t.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = __fmul2_rn(wv[i], sv[i]);                  // Ws = W * s
+    float mn = dq_fmin_nan(x[0].x, x[0].y), mx = dq_fmax_nan(x[0].x, x[0].y);
+#pragma unroll
+    for (int i = 1; i < 16; ++i) {
+      mn = dq_fmin_nan(mn, dq_fmin_nan(x[i].x, x[i].y));
+      mx = dq_fmax_nan(mx, dq_fmax_nan(x[i].x, x[i].y));
+    }
+#pragma unroll
+    for (int m = 1; m < LPG; m <<= 1) {
+      mn = dq_fmin_nan(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, m));
+      mx = dq_fmax_nan(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
+    }
+    const FastGroup fg = group_params_fast<AR_F32, BITS>(mn, mx, sym, qmin, qmax);
+    uint32_t o[16];
+    if (fg.ok) {
+      const float2 r2 = make_float2(fg.rcp, fg.rcp), ns2 = make_float2(-fg.scale, -fg.scale);
+      const float2 zp2 = make_float2(fg.zp, fg.zp), nzp2 = make_float2(-fg.zp, -fg.zp);
+      const float2 sc2 = make_float2(fg.scale, fg.scale);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 q0 = __fmul2_rn(x[i], r2);
+        const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x[i]), r2, q0);            // x / scale, exact
+        float2 v = __fadd2_rn(q, zp2);
+        v.x = fminf(fmaxf(v.x, qmin), qmax);                                       // clamp commutes with rint
+        v.y = fminf(fmaxf(v.y, qmin), qmax);
+        const float2 qf = __fadd2_rn(__fadd2_rn(v, magic2), nmagic2);              // rint (half-to-even)
+        const float2 d = __fmul2_rn(__fadd2_rn(qf, nzp2), sc2);                    // (q - zp) * scale
+        const int c4 = i >> 1;
+        const float4 rr = __ldg(rp + c4);
+        const float2 rs = (i & 1) ? make_float2(rr.z, rr.w) : make_float2(rr.x, rr.y);
+        const float2 h0 = __fmul2_rn(d, rs);
+        const float2 nsv = make_float2(-sv[i].x, -sv[i].y);
+        const float2 what = __ffma2_rn(__ffma2_rn(nsv, h0, d), rs, h0);            // deq / s, exact
+        const float2 dl = __fadd2_rn(wv[i], make_float2(-what.x, -what.y));        // W - W^
+        const __nv_bfloat162 b = __float22bfloat162_rn(dl);
+        o[i] = *reinterpret_cast<const uint32_t*>(&b);
+      }
+    } else {
+      const GroupParams gp = group_params<AR_F32>(mn, mx, sym, qmin, qmax);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float d2[2];
+        const float xs[2] = {x[i].x, x[i].y}, ss[2] = {sv[i].x, sv[i].y}, ww[2] = {wv[i].x, wv[i].y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float r = rintf(__fadd_rn(__fdiv_rn(xs[h], gp.scale), gp.zp));
+          const float qf = (r != r) ? r : fminf(fmaxf(r, qmin), qmax);
+          d2[h] = __fsub_rn(ww[h], __fdiv_rn(__fmul_rn(__fsub_rn(qf, gp.zp), gp.scale), ss[h]));
+        }
+        const __nv_bfloat162 b = __floats2bfloat162_rn(d2[0], d2[1]);
+        o[i] = *reinterpret_cast<const uint32_t*>(&b);
+      }
+    }
+    if (valid) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (int64_t)a * plane);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[c] = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+    }
   }
 }
 
@@ -470,6 +607,24 @@ extern "C" int awqk_alpha_grid(const double* colsum, int64_t T, int64_t K, int n
 }
 
 template <typename T>
+static int launch_delta_v2(const T* w, int64_t C, int64_t K, int g, int bits, bool sym, const float* s, float* r,
+                           int n_s, __nv_bfloat16* dw, cudaStream_t st) {
+  const int64_t ns = (int64_t)n_s * K;
+  rcp_grid_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(s, ns, r);
+  dim3 grid((unsigned)ceil_div(K, 1024), (unsigned)ceil_div(C, 8));
+  if (grid.y > 65535) return AWQK_E_BADARG;
+#define AWQK_DELTA2(GG, BB) fakequant_delta_v2<T, GG, BB><<<grid, 256, 0, st>>>(w, C, K, sym, s, r, n_s, dw)
+  if (bits == 4) {
+    if (g == 32) AWQK_DELTA2(32, 4); else if (g == 64) AWQK_DELTA2(64, 4); else AWQK_DELTA2(128, 4);
+  } else {
+    if (g == 32) AWQK_DELTA2(32, 8); else if (g == 64) AWQK_DELTA2(64, 8); else AWQK_DELTA2(128, 8);
+  }
+#undef AWQK_DELTA2
+  AWQK_CUDA(cudaGetLastError());
+  return AWQK_OK;
+}
+
+template <typename T>
 static int launch_delta(const T* w, int64_t n, int64_t K, int g, int bits, bool sym, const float* s, int n_s,
                         __nv_bfloat16* dw, cudaStream_t st) {
   const int64_t ctas = ceil_div(n, 256 * 8);
@@ -486,7 +641,8 @@ static int launch_delta(const T* w, int64_t n, int64_t K, int g, int bits, bool 
 }
 
 extern "C" int awqk_fakequant_delta(const void* w, int dtype, int64_t C, int64_t K, int group_size, int bits,
-                                    int symmetric, const float* s, int n_s, void* dw_bf16, void* stream) {
+                                    int symmetric, const float* s, int n_s, void* dw_bf16, float* rcp_workspace,
+                                    void* stream) {
   if (!w || !s || !dw_bf16 || C <= 0 || K <= 0 || n_s <= 0 || (bits != 4 && bits != 8)) return AWQK_E_BADARG;
   if (!(group_size == 32 || group_size == 64 || group_size == 128) || (K % group_size) != 0) return AWQK_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(dw_bf16)) & 15u)
@@ -496,6 +652,16 @@ extern "C" int awqk_fakequant_delta(const void* w, int dtype, int64_t C, int64_t
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   auto out = reinterpret_cast<__nv_bfloat16*>(dw_bf16);
   const bool sym = symmetric != 0;
+  if (rcp_workspace != nullptr && (K % 32) == 0 && ceil_div(C, 8) <= 65535) {
+    if ((reinterpret_cast<uintptr_t>(rcp_workspace) & 15u) != 0) return AWQK_E_ALIGN;
+    if (dtype == AWQK_BF16)
+      return launch_delta_v2(reinterpret_cast<const __nv_bfloat16*>(w), C, K, group_size, bits, sym, s, rcp_workspace, n_s, out, st);
+    if (dtype == AWQK_FP16)
+      return launch_delta_v2(reinterpret_cast<const __half*>(w), C, K, group_size, bits, sym, s, rcp_workspace, n_s, out, st);
+    if (dtype == AWQK_FP32)
+      return launch_delta_v2(reinterpret_cast<const float*>(w), C, K, group_size, bits, sym, s, rcp_workspace, n_s, out, st);
+    return AWQK_E_UNSUPPORTED;
+  }
   if (dtype == AWQK_BF16)
     return launch_delta(reinterpret_cast<const __nv_bfloat16*>(w), C * K, K, group_size, bits, sym, s, n_s, out, st);
   if (dtype == AWQK_FP16)
@@ -544,7 +710,15 @@ extern "C" int awqk_sqerr_gemm(const void* x_bf16, const void* dw_bf16, int64_t 
   AWQK_CUDA(cudaGetDevice(&dev));
   AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t smem = (size_t)kGStages * kStageBytes + 1024 + 256;
-  AWQK_CUDA(cudaFuncSetAttribute(sqerr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    // the opt-in is per device; set it once per device (atomic bit mask, immutable afterwards)
+    static std::atomic<uint64_t> configured{0};
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+      AWQK_CUDA(cudaFuncSetAttribute(sqerr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured.fetch_or(bit, std::memory_order_release);
+    }
+  }
   const unsigned grid = (unsigned)std::min<int64_t>(total, sms);
   sqerr_gemm_kernel<<<grid, kGemmThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(map_x, map_dw, n_s, m_tiles,
                                                                                          n_tiles, k_blocks, err);

@@ -232,19 +232,36 @@ def run_native(args):
                          torch.empty((C, G), dtype=torch.int32, device=dev),
                          torch.empty((C, -(-G // per)), dtype=torch.int32, device=dev))
     arith = N.ARITH_FP32 if args.arith == "fp32" else N.ARITH_NATIVE
-    st = torch.cuda.current_stream(dev).cuda_stream
     launches_per_step = 1 + 2 * len(d_single)
 
     def k1_arena():
+        st = torch.cuda.current_stream(dev).cuda_stream
         N.check(L.awqk_group_quant(d_arena.data_ptr(), N.BF16, 1, n_arena, g, bits, int(sym), arith, None,
                                    d_q.data_ptr(), d_s.data_ptr(), None, d_zq.data_ptr(), None, st))
 
-    def step_device():
+    def step_launches():
+        st = torch.cuda.current_stream(dev).cuda_stream
         k1_arena()
         for n, t in d_single.items():
             C, K, qw, sc, zp, zq = single_out[n]
             N.check(L.awqk_group_quant(t.data_ptr(), N.BF16, C, K, g, bits, int(sym), arith, None, qw.data_ptr(),
                                        sc.data_ptr(), zp.data_ptr(), zq.data_ptr(), None, st))
+
+    # one pass = one CUDA graph launch (the per-tensor launches are captured once, replayed per step)
+    step_device, graph_mode = step_launches, "direct launches"
+    try:
+        step_launches()
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            step_launches()
+        graph.replay()
+        torch.cuda.synchronize(dev)
+        step_device, graph_mode = graph.replay, "CUDA graph replay"
+    except Exception as e:      # capture is an optimisation of the launch path only
+        graph_mode = f"direct launches (graph capture failed: {str(e)[:80]})"
+        torch.cuda.synchronize(dev)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -329,7 +346,7 @@ def run_native(args):
                                f"{'symmetric' if sym else 'asymmetric'}, arith={args.arith}",
                    "tensors_per_rank": len(shapes), "params_per_rank": payload_elems,
                    "l2": "inputs larger than L2 (arena %.0f MB per pass)" % (n_arena * 2 / 1e6),
-                   "parallelism": f"tensor-sharded x{world}, no data-path collective"},
+                   "parallelism": f"tensor-sharded x{world}, no data-path collective", "launch": graph_mode},
         "s_per_model": ms_step * 1e-3, "roofline": roofline,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "s_per_model": dt / e2e_steps, "api": "AWQQuantizer.quantize_model(HostArena, pack=True)"},

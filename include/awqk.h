@@ -120,9 +120,12 @@ AWQK_API int awqk_alpha_grid(const double* colsum, int64_t T, int64_t K, int n_g
                     float* workspace_2n, void* stream);
 
 /* dW[i] = bf16( W - dequant(group_quant(W * s_i)) / s_i ), i = 0..n_s-1; fp32 arithmetic.
- *   w [C,K] bf16/fp16/fp32;  s [n_s, K] fp32;  dw bf16 [n_s, C, K].  K % group_size == 0. */
+ *   w [C,K] bf16/fp16/fp32;  s [n_s, K] fp32;  dw bf16 [n_s, C, K].  K % group_size == 0.
+ *   rcp_workspace: nullable, n_s*K floats; when given (and K % 32 == 0) the packed-math kernel runs
+ *   (it stores the refined reciprocals of s there); results are identical either way. */
 AWQK_API int awqk_fakequant_delta(const void* w, int dtype, int64_t C, int64_t K, int group_size, int bits,
-                         int symmetric, const float* s, int n_s, void* dw_bf16, void* stream);
+                         int symmetric, const float* s, int n_s, void* dw_bf16, float* rcp_workspace,
+                         void* stream);
 
 /* err[i] += sum over [T, C] of (X . dW_i^T)^2, tcgen05 bf16 GEMM with fp32 TMEM accumulators and a
  * fused sum-of-squares epilogue.  X [T,K] bf16, dW [n_s, C, K] bf16, err fp64 [n_s] (zeroed by the

@@ -57,13 +57,15 @@ def test_fakequant_delta_bit_exact(native_lib, cuda_device, dt, sym, g):
     m = O.activation_mean(X)
     s = torch.stack([O.alpha_scales(m, a) for a in (0.0, 0.35, 0.8)])
     wd, sd = W.to(cuda_device), s.to(cuda_device)
-    dw = torch.empty((n_s, C, K), dtype=torch.bfloat16, device=cuda_device)
-    assert native_lib.awqk_fakequant_delta(wd.data_ptr(), N.dtype_code(wd.dtype), C, K, g, 4, int(sym), sd.data_ptr(),
-                                           n_s, dw.data_ptr(), None) == 0
-    torch.cuda.synchronize()
-    for i in range(n_s):
-        want = O.fake_quant_delta(W, s[i], 4, g, sym).to(torch.bfloat16)
-        assert_same(dw[i].cpu().view(torch.int16), want.view(torch.int16), f"dW[{i}]")
+    rws = torch.empty((n_s, K), dtype=torch.float32, device=cuda_device)
+    for ws_ptr, tag in ((None, "register kernel"), (rws.data_ptr(), "packed kernel")):
+        dw = torch.zeros((n_s, C, K), dtype=torch.bfloat16, device=cuda_device)
+        assert native_lib.awqk_fakequant_delta(wd.data_ptr(), N.dtype_code(wd.dtype), C, K, g, 4, int(sym),
+                                               sd.data_ptr(), n_s, dw.data_ptr(), ws_ptr, None) == 0
+        torch.cuda.synchronize()
+        for i in range(n_s):
+            want = O.fake_quant_delta(W, s[i], 4, g, sym).to(torch.bfloat16)
+            assert_same(dw[i].cpu().view(torch.int16), want.view(torch.int16), f"dW[{i}] {tag}")
 
 
 @pytest.mark.parametrize("T,C,K,n_s", [(128, 256, 64, 1), (256, 512, 256, 3), (200, 300, 320, 2), (512, 1024, 1024, 5),
