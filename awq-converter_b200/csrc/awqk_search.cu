@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "awqk_common.cuh"
 
@@ -247,14 +248,30 @@ __device__ __forceinline__ void load32<float>(const float* p, float2 (&f)[16]) {
   }
 }
 
+// The 1024-column slab of s_a and 1/s_a is fetched ONCE per CTA and alpha with coalesced 16-byte
+// loads (one per thread and array) into shared memory; every thread then reads its 32 floats with
+// conflict-free LDS.128 (chunk c of lane l is stored at position (c + l) % 8 of the lane's 128-byte
+// row).  Reading 128 contiguous bytes per lane straight from global memory costs 32 L1 wavefronts per
+// load instruction and made the first version of this kernel L1-wavefront bound (741 GB/s written).
 template <typename T, int G, int BITS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 fakequant_delta_v2(const T* __restrict__ w, int64_t C, int64_t K, bool sym, const float* __restrict__ s_grid,
-                   const float* __restrict__ r_grid, int n_s, __nv_bfloat16* __restrict__ dw) {
+                   const float* __restrict__ r_grid, int n_s_total, __nv_bfloat16* __restrict__ dw) {
   constexpr int LPG = G / 32;
+  // blockIdx.z owns a contiguous slice of the alpha grid (more CTAs in flight for small tensors)
+  const int per_z = (n_s_total + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int a_begin = (int)blockIdx.z * per_z;
+  const int n_s = min(per_z, n_s_total - a_begin);
+  if (n_s <= 0) return;
+  s_grid += (int64_t)a_begin * K;
+  r_grid += (int64_t)a_begin * K;
+  dw += (int64_t)a_begin * C * K;
+  __shared__ __align__(16) float sm_s[2][1024];
+  __shared__ __align__(16) float sm_r[2][1024];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.y * 8 + warp;
-  const int64_t col = (int64_t)blockIdx.x * 1024 + lane * 32;
+  const int64_t col0 = (int64_t)blockIdx.x * 1024;
+  const int64_t col = col0 + lane * 32;
   const bool valid = row < C && col < K;
   const float qmin = sym ? -(float)(1 << (BITS - 1)) : 0.0f;
   const float qmax = sym ? (float)((1 << (BITS - 1)) - 1) : (float)((1 << BITS) - 1);
@@ -265,19 +282,38 @@ fakequant_delta_v2(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
 #pragma unroll
     for (int i = 0; i < 16; ++i) wv[i] = make_float2(0.0f, 0.0f);
   }
-  const int64_t cc = valid ? col : 0;
+  // staging: thread t fetches floats [4t, 4t+4) of the slab -> owner lane t/8, chunk t%8
+  const int t = threadIdx.x;
+  const int64_t gcol = col0 + 4 * t;
+  const bool gvalid = gcol < K;                       // K % 32 == 0 -> a float4 is fully valid or not
+  const int st_off = (t >> 3) * 32 + (((t & 7) + (t >> 3)) & 7) * 4;      // float index in the slab buffer
+  int ld_off[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) ld_off[c] = lane * 32 + ((c + lane) & 7) * 4;
+
   __nv_bfloat16* out = dw + row * K + col;
   const int64_t plane = C * K;
+  float4 ns = make_float4(1.f, 1.f, 1.f, 1.f), nr = ns;
+  if (gvalid) {
+    ns = __ldg(reinterpret_cast<const float4*>(s_grid + gcol));
+    nr = __ldg(reinterpret_cast<const float4*>(r_grid + gcol));
+  }
 #pragma unroll 1
   for (int a = 0; a < n_s; ++a) {
-    const float4* sp = reinterpret_cast<const float4*>(s_grid + (int64_t)a * K + cc);
-    const float4* rp = reinterpret_cast<const float4*>(r_grid + (int64_t)a * K + cc);
+    const int buf = a & 1;
+    *reinterpret_cast<float4*>(&sm_s[buf][st_off]) = ns;
+    *reinterpret_cast<float4*>(&sm_r[buf][st_off]) = nr;
+    __syncthreads();                                  // slab a visible; buffer buf^1 is free again after this point
+    if (a + 1 < n_s && gvalid) {                      // prefetch the next alpha's slab while computing this one
+      ns = __ldg(reinterpret_cast<const float4*>(s_grid + (int64_t)(a + 1) * K + gcol));
+      nr = __ldg(reinterpret_cast<const float4*>(r_grid + (int64_t)(a + 1) * K + gcol));
+    }
     float2 sv[16], x[16];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const float4 t = __ldg(sp + c);
-      sv[2 * c] = make_float2(t.x, t.y);
-      sv[2 * c + 1] = make_float2(t.z, t.w);
+      const float4 v = *reinterpret_cast<const float4*>(&sm_s[buf][ld_off[c]]);
+      sv[2 * c] = make_float2(v.x, v.y);
+      sv[2 * c + 1] = make_float2(v.z, v.w);
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = __fmul2_rn(wv[i], sv[i]);                  // Ws = W * s
@@ -299,23 +335,26 @@ fakequant_delta_v2(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
       const float2 zp2 = make_float2(fg.zp, fg.zp), nzp2 = make_float2(-fg.zp, -fg.zp);
       const float2 sc2 = make_float2(fg.scale, fg.scale);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float2 q0 = __fmul2_rn(x[i], r2);
-        const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x[i]), r2, q0);            // x / scale, exact
-        float2 v = __fadd2_rn(q, zp2);
-        v.x = fminf(fmaxf(v.x, qmin), qmax);                                       // clamp commutes with rint
-        v.y = fminf(fmaxf(v.y, qmin), qmax);
-        const float2 qf = __fadd2_rn(__fadd2_rn(v, magic2), nmagic2);              // rint (half-to-even)
-        const float2 d = __fmul2_rn(__fadd2_rn(qf, nzp2), sc2);                    // (q - zp) * scale
-        const int c4 = i >> 1;
-        const float4 rr = __ldg(rp + c4);
-        const float2 rs = (i & 1) ? make_float2(rr.z, rr.w) : make_float2(rr.x, rr.y);
-        const float2 h0 = __fmul2_rn(d, rs);
-        const float2 nsv = make_float2(-sv[i].x, -sv[i].y);
-        const float2 what = __ffma2_rn(__ffma2_rn(nsv, h0, d), rs, h0);            // deq / s, exact
-        const float2 dl = __fadd2_rn(wv[i], make_float2(-what.x, -what.y));        // W - W^
-        const __nv_bfloat162 b = __float22bfloat162_rn(dl);
-        o[i] = *reinterpret_cast<const uint32_t*>(&b);
+      for (int c = 0; c < 8; ++c) {
+        const float4 rr = *reinterpret_cast<const float4*>(&sm_r[buf][ld_off[c]]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = 2 * c + h;
+          const float2 rs = h ? make_float2(rr.z, rr.w) : make_float2(rr.x, rr.y);
+          const float2 q0 = __fmul2_rn(x[i], r2);
+          const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x[i]), r2, q0);          // x / scale, exact
+          float2 v = __fadd2_rn(q, zp2);
+          v.x = fminf(fmaxf(v.x, qmin), qmax);                                     // clamp commutes with rint
+          v.y = fminf(fmaxf(v.y, qmin), qmax);
+          const float2 qf = __fadd2_rn(__fadd2_rn(v, magic2), nmagic2);            // rint (half-to-even)
+          const float2 d = __fmul2_rn(__fadd2_rn(qf, nzp2), sc2);                  // (q - zp) * scale
+          const float2 h0 = __fmul2_rn(d, rs);
+          const float2 nsv = make_float2(-sv[i].x, -sv[i].y);
+          const float2 what = __ffma2_rn(__ffma2_rn(nsv, h0, d), rs, h0);          // deq / s, exact
+          const float2 dl = __fadd2_rn(wv[i], make_float2(-what.x, -what.y));      // W - W^
+          const __nv_bfloat162 b = __float22bfloat162_rn(dl);
+          o[i] = *reinterpret_cast<const uint32_t*>(&b);
+        }
       }
     } else {
       const GroupParams gp = group_params<AR_F32>(mn, mx, sym, qmin, qmax);
@@ -336,7 +375,180 @@ fakequant_delta_v2(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
     if (valid) {
       uint4* dst = reinterpret_cast<uint4*>(out + (int64_t)a * plane);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) dst[c] = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+      for (int c = 0; c < 4; ++c) st_stream16(dst + c, make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]));
+    }
+  }
+}
+
+// 32 consecutive elements of a W row, kept in the narrowest register form
+template <typename T>
+struct Row32;
+template <>
+struct Row32<__nv_bfloat16> {
+  uint32_t r[16];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + c);
+      r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+    }
+  }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = 0u;
+  }
+  __device__ __forceinline__ float2 f2(int i) const {
+    return make_float2(__uint_as_float(r[i] << 16), __uint_as_float(r[i] & 0xFFFF0000u));
+  }
+};
+template <>
+struct Row32<__half> {
+  uint32_t r[16];
+  __device__ __forceinline__ void load(const __half* p) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + c);
+      r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+    }
+  }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = 0u;
+  }
+  __device__ __forceinline__ float2 f2(int i) const { return __half22float2(*reinterpret_cast<const __half2*>(&r[i])); }
+};
+template <>
+struct Row32<float> {
+  float2 r[16];
+  __device__ __forceinline__ void load(const float* p) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p) + c);
+      r[2 * c] = make_float2(v.x, v.y);
+      r[2 * c + 1] = make_float2(v.z, v.w);
+    }
+  }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = make_float2(0.0f, 0.0f);
+  }
+  __device__ __forceinline__ float2 f2(int i) const { return r[i]; }
+};
+
+// ---- v3: scale slab in REGISTERS, rows streamed.  A warp keeps s_a / (1/s_a) for its 1024 columns
+// in registers and walks `rows_per_warp` rows of W for that alpha: no shared memory (leaves the
+// shared-memory bandwidth to a concurrently running GEMM), no block barrier per alpha, the strided
+// slab loads amortised over the rows.  W is re-read once per alpha from L2.
+template <typename T, int G, int BITS>
+__global__ void __launch_bounds__(256, 2)
+fakequant_delta_v3(const T* __restrict__ w, int64_t C, int64_t K, bool sym, const float* __restrict__ s_grid,
+                   const float* __restrict__ r_grid, int n_s_total, __nv_bfloat16* __restrict__ dw,
+                   int rows_per_warp) {
+  constexpr int LPG = G / 32;
+  const int per_z = (n_s_total + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int a_begin = (int)blockIdx.z * per_z;
+  const int n_s = min(per_z, n_s_total - a_begin);
+  if (n_s <= 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row0 = ((int64_t)blockIdx.y * 8 + warp) * rows_per_warp;
+  const int64_t col = (int64_t)blockIdx.x * 1024 + lane * 32;
+  const bool cvalid = col < K;
+  const int64_t cc = cvalid ? col : 0;
+  const float qmin = sym ? -(float)(1 << (BITS - 1)) : 0.0f;
+  const float qmax = sym ? (float)((1 << (BITS - 1)) - 1) : (float)((1 << BITS) - 1);
+  const float2 magic2 = make_float2(12582912.0f, 12582912.0f), nmagic2 = make_float2(-12582912.0f, -12582912.0f);
+  const int64_t plane = C * K;
+  int64_t row_end = row0 + rows_per_warp;
+  if (row_end > C) row_end = C;
+#pragma unroll 1
+  for (int a = a_begin; a < a_begin + n_s; ++a) {
+    float2 sv[16], rv[16];
+    {
+      const float4* sp = reinterpret_cast<const float4*>(s_grid + (int64_t)a * K + cc);
+      const float4* rp = reinterpret_cast<const float4*>(r_grid + (int64_t)a * K + cc);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 u = __ldg(sp + c), v = __ldg(rp + c);
+        sv[2 * c] = make_float2(u.x, u.y); sv[2 * c + 1] = make_float2(u.z, u.w);
+        rv[2 * c] = make_float2(v.x, v.y); rv[2 * c + 1] = make_float2(v.z, v.w);
+      }
+    }
+    __nv_bfloat16* outp = dw + (int64_t)a * plane + col;
+#pragma unroll 1
+    for (int64_t row = row0; row < row_end; ++row) {
+      Row32<T> wr;
+      if (cvalid) wr.load(w + row * K + col); else wr.zero();
+      float mn, mx;
+      {
+        const float2 x0 = __fmul2_rn(wr.f2(0), sv[0]);
+        mn = dq_fmin_nan(x0.x, x0.y);
+        mx = dq_fmax_nan(x0.x, x0.y);
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+          const float2 x = __fmul2_rn(wr.f2(i), sv[i]);
+          mn = dq_fmin_nan(mn, dq_fmin_nan(x.x, x.y));
+          mx = dq_fmax_nan(mx, dq_fmax_nan(x.x, x.y));
+        }
+      }
+#pragma unroll
+      for (int m = 1; m < LPG; m <<= 1) {
+        mn = dq_fmin_nan(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, m));
+        mx = dq_fmax_nan(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
+      }
+      const FastGroup fg = group_params_fast<AR_F32, BITS>(mn, mx, sym, qmin, qmax);
+      uint4* dst = reinterpret_cast<uint4*>(outp + row * K);
+      if (fg.ok) {
+        const float2 r2 = make_float2(fg.rcp, fg.rcp), ns2 = make_float2(-fg.scale, -fg.scale);
+        const float2 zp2 = make_float2(fg.zp, fg.zp), nzp2 = make_float2(-fg.zp, -fg.zp);
+        const float2 sc2 = make_float2(fg.scale, fg.scale);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = 4 * c + j;
+            const float2 wf = wr.f2(i);
+            const float2 x = __fmul2_rn(wf, sv[i]);                                   // Ws = W * s
+            const float2 q0 = __fmul2_rn(x, r2);
+            const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x), r2, q0);              // x / scale, exact
+            float2 v = __fadd2_rn(q, zp2);
+            v.x = fminf(fmaxf(v.x, qmin), qmax);
+            v.y = fminf(fmaxf(v.y, qmin), qmax);
+            const float2 qf = __fadd2_rn(__fadd2_rn(v, magic2), nmagic2);             // rint (half-to-even)
+            const float2 d = __fmul2_rn(__fadd2_rn(qf, nzp2), sc2);                   // (q - zp) * scale
+            const float2 h0 = __fmul2_rn(d, rv[i]);
+            const float2 nsv = make_float2(-sv[i].x, -sv[i].y);
+            const float2 what = __ffma2_rn(__ffma2_rn(nsv, h0, d), rv[i], h0);        // deq / s, exact
+            const float2 dl = __fadd2_rn(wf, make_float2(-what.x, -what.y));          // W - W^
+            const __nv_bfloat162 b = __float22bfloat162_rn(dl);
+            o[j] = *reinterpret_cast<const uint32_t*>(&b);
+          }
+          if (cvalid) st_stream16(dst + c, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      } else {
+        const GroupParams gp = group_params<AR_F32>(mn, mx, sym, qmin, qmax);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = 4 * c + j;
+            float d2[2];
+            const float2 wf = wr.f2(i);
+            const float ss[2] = {sv[i].x, sv[i].y}, ww[2] = {wf.x, wf.y};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float xs = __fmul_rn(ww[h], ss[h]);
+              const float r = rintf(__fadd_rn(__fdiv_rn(xs, gp.scale), gp.zp));
+              const float qf = (r != r) ? r : fminf(fmaxf(r, qmin), qmax);
+              d2[h] = __fsub_rn(ww[h], __fdiv_rn(__fmul_rn(__fsub_rn(qf, gp.zp), gp.scale), ss[h]));
+            }
+            const __nv_bfloat162 b = __floats2bfloat162_rn(d2[0], d2[1]);
+            o[j] = *reinterpret_cast<const uint32_t*>(&b);
+          }
+          if (cvalid) st_stream16(dst + c, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+      }
     }
   }
 }
@@ -611,9 +823,43 @@ static int launch_delta_v2(const T* w, int64_t C, int64_t K, int g, int bits, bo
                            int n_s, __nv_bfloat16* dw, cudaStream_t st) {
   const int64_t ns = (int64_t)n_s * K;
   rcp_grid_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(s, ns, r);
-  dim3 grid((unsigned)ceil_div(K, 1024), (unsigned)ceil_div(C, 8));
+  // default: v2 (shared-memory slab; 1.6 TB/s written).  AWQK_DELTA_V3=1 selects the register-slab
+  // variant (no shared memory, slower stand-alone: 1.3 TB/s) for A/B measurements.
+  static const bool use_v3 = []() { const char* e = getenv("AWQK_DELTA_V3"); return e && e[0] == '1'; }();
+  if (use_v3) {
+    const int z = std::min(n_s, 4);
+    const int64_t slabs = ceil_div(K, 1024);
+    // rows per warp: amortise the slab loads (>= 8 rows) but keep >= ~4 CTAs per SM in flight
+    int64_t rpw = 32;
+    while (rpw > 8 && slabs * ceil_div(C, 8 * rpw) * z < 600) rpw >>= 1;
+    dim3 g3((unsigned)slabs, (unsigned)ceil_div(C, 8 * rpw), (unsigned)z);
+    if (g3.y > 65535) return AWQK_E_BADARG;
+#define AWQK_DELTA3(GG, BB) fakequant_delta_v3<T, GG, BB><<<g3, 256, 0, st>>>(w, C, K, sym, s, r, n_s, dw, (int)rpw)
+    if (bits == 4) {
+      if (g == 32) AWQK_DELTA3(32, 4); else if (g == 64) AWQK_DELTA3(64, 4); else AWQK_DELTA3(128, 4);
+    } else {
+      if (g == 32) AWQK_DELTA3(32, 8); else if (g == 64) AWQK_DELTA3(64, 8); else AWQK_DELTA3(128, 8);
+    }
+#undef AWQK_DELTA3
+    AWQK_CUDA(cudaGetLastError());
+    return AWQK_OK;
+  }
+  dim3 grid((unsigned)ceil_div(K, 1024), (unsigned)ceil_div(C, 8), (unsigned)std::min(n_s, 4));
   if (grid.y > 65535) return AWQK_E_BADARG;
-#define AWQK_DELTA2(GG, BB) fakequant_delta_v2<T, GG, BB><<<grid, 256, 0, st>>>(w, C, K, sym, s, r, n_s, dw)
+  // Same shared-memory carve-out as the GEMM (max shared): SMs do not have to be drained and
+  // re-configured between the two kernels, so delta(i+1) co-resides with the GEMM of tensor i.
+#define AWQK_DELTA2(GG, BB)                                                                                     \
+  do {                                                                                                          \
+    static std::atomic<uint64_t> cfg{0};                                                                        \
+    int dev_ = 0;                                                                                               \
+    AWQK_CUDA(cudaGetDevice(&dev_));                                                                            \
+    if (!(cfg.load(std::memory_order_acquire) & (1ull << (dev_ & 63)))) {                                       \
+      AWQK_CUDA(cudaFuncSetAttribute(fakequant_delta_v2<T, GG, BB>, cudaFuncAttributePreferredSharedMemoryCarveout, \
+                                     (int)cudaSharedmemCarveoutMaxShared));                                     \
+      cfg.fetch_or(1ull << (dev_ & 63), std::memory_order_release);                                             \
+    }                                                                                                           \
+    fakequant_delta_v2<T, GG, BB><<<grid, 256, 0, st>>>(w, C, K, sym, s, r, n_s, dw);                          \
+  } while (0)
   if (bits == 4) {
     if (g == 32) AWQK_DELTA2(32, 4); else if (g == 64) AWQK_DELTA2(64, 4); else AWQK_DELTA2(128, 4);
   } else {
