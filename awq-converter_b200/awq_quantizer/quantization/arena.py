@@ -22,8 +22,8 @@ from .. import _native as N
 TILE = 8192  # elements; K1's CTA tile and the pipeline's chunk quantum
 
 
-def arena_eligible(shape, dtype, group_size: int, bits: int) -> bool:
-    """flat layout + flat zero-point packing: rows are whole groups and whole packed zero words"""
+def pipe_eligible(shape, dtype, group_size: int, bits: int) -> bool:
+    """the host pipeline (awqk_pipe_quant_host) handles every tensor whose rows are whole groups"""
     if dtype not in (torch.bfloat16, torch.float16, torch.float32):
         return False
     if group_size not in (32, 64, 128):
@@ -34,9 +34,18 @@ def arena_eligible(shape, dtype, group_size: int, bits: int) -> bool:
     if n < group_size or n == 0:
         return False
     rows = 1 if len(shape) <= 1 else shape[0]
-    k = n // rows
-    per = 32 // bits
-    return k % group_size == 0 and (k // group_size) % per == 0
+    return (n // rows) % group_size == 0
+
+
+def arena_eligible(shape, dtype, group_size: int, bits: int) -> bool:
+    """flat layout + flat zero-point packing: rows are whole groups AND whole packed zero words"""
+    if not pipe_eligible(shape, dtype, group_size, bits):
+        return False
+    n = 1
+    for s in shape:
+        n *= s
+    rows = 1 if len(shape) <= 1 else shape[0]
+    return ((n // rows) // group_size) % (32 // bits) == 0
 
 
 class HostArena:
@@ -139,6 +148,40 @@ def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: b
     if sync:
         N.check(L.awqk_pipe_sync(pipe), "awqk_pipe_sync")
     return results
+
+
+def quantize_rows_pipelined(t: torch.Tensor, *, bits: int, group_size: int, symmetric: bool, arith: str,
+                            device: torch.device, chunk_bytes: int = 32 << 20, sync: bool = True) -> Dict[str, torch.Tensor]:
+    """One host tensor whose rows are whole groups but not whole packed-zero words (e.g. K = 512 at
+    g = 128): chunked by rows through the same pipeline; packed zero points are padded per row."""
+    per = 32 // bits
+    pin = torch.cuda.is_available()
+    src = t.contiguous()
+    if pin and not src.is_pinned():
+        staged = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        staged.copy_(src)
+        src = staged
+    rows = 1 if src.dim() <= 1 else src.shape[0]
+    k = src.numel() // rows
+    g = k // group_size
+    out = {
+        "qweight": torch.empty((rows, k // per), dtype=torch.int32, pin_memory=pin),
+        "qzeros": torch.empty((rows, -(-g // per)), dtype=torch.int32, pin_memory=pin),
+        "scales": torch.empty((rows, g), dtype=torch.float16, pin_memory=pin),
+        "bits": torch.tensor(bits, dtype=torch.int32),
+        "group_size": torch.tensor(group_size, dtype=torch.int32),
+        "symmetric": torch.tensor(symmetric, dtype=torch.bool),
+    }
+    pipe = _PipeHandle.get(device.index if device.index is not None else torch.cuda.current_device(), chunk_bytes)
+    L = N.lib()
+    N.check(L.awqk_pipe_quant_host(pipe, src.data_ptr(), N.dtype_code(src.dtype), rows, k, group_size, bits,
+                                   int(symmetric), N.ARITH_FP32 if arith == "fp32" else N.ARITH_NATIVE, None,
+                                   out["qweight"].data_ptr(), out["scales"].data_ptr(), None, out["qzeros"].data_ptr()),
+            "awqk_pipe_quant_host")
+    out["_keepalive"] = src
+    if sync:
+        N.check(L.awqk_pipe_sync(pipe), "awqk_pipe_sync")
+    return out
 
 
 def sync_pipe(device: torch.device, chunk_bytes: int = 32 << 20) -> None:

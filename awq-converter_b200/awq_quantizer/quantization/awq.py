@@ -200,7 +200,8 @@ class AWQQuantizer:
                     continue
             return quantized
 
-        from .arena import HostArena, arena_eligible, quantize_arena
+        from .arena import (HostArena, arena_eligible, pipe_eligible, quantize_arena, quantize_rows_pipelined,
+                            sync_pipe)
         dev = self._cuda_device()
         self._check_zero_point_mode()
         quantized = {}
@@ -220,8 +221,20 @@ class AWQQuantizer:
         if arena is not None:
             quantized.update(quantize_arena(arena, bits=self.bits, group_size=self.group_size,
                                             symmetric=self.symmetric, arith=self.arith, device=dev,
-                                            chunk_bytes=chunk_bytes))
-        for name, tensor in singles.items():
+                                            chunk_bytes=chunk_bytes, sync=False))
+        rest = {}
+        for name, tensor in singles.items():           # rows of whole groups: same pipeline, chunked by rows
+            if isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu" and \
+                    pipe_eligible(tuple(tensor.shape), tensor.dtype, self.group_size, self.bits):
+                r = quantize_rows_pipelined(tensor, bits=self.bits, group_size=self.group_size, symmetric=self.symmetric,
+                                            arith=self.arith, device=dev, chunk_bytes=chunk_bytes, sync=False)
+                quantized[name] = r
+            else:
+                rest[name] = tensor
+        sync_pipe(dev, chunk_bytes)
+        for r in quantized.values():
+            r.pop("_keepalive", None)
+        for name, tensor in rest.items():              # ragged rows, odd group sizes, fp64, numel < group_size ...
             try:
                 quantized[name] = self.quantize(tensor, pack=True, keep_unpacked=False)
             except Exception as e:

@@ -70,7 +70,7 @@ static int pipe_create_impl(awqk_pipe* p) {
     AWQK_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_qp[b]), e));            // 8 bit worst case
     AWQK_CUDA(cudaMalloc(&p->d_sc[b], e / 32 * 2));
     AWQK_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_zp[b]), e / 32 * 4));
-    AWQK_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_zpp[b]), e / 32 + 16));
+    AWQK_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_zpp[b]), e / 8 + 16));   // row mode: <= one word per group
     AWQK_CUDA(cudaEventCreateWithFlags(&p->ev_in[b], cudaEventDisableTiming));
     AWQK_CUDA(cudaEventCreateWithFlags(&p->ev_k[b], cudaEventDisableTiming));
     AWQK_CUDA(cudaEventCreateWithFlags(&p->ev_out[b], cudaEventDisableTiming));
@@ -119,12 +119,51 @@ extern "C" int awqk_pipe_quant_host(awqk_pipe* p, const void* w_host, int dtype,
     return AWQK_E_UNSUPPORTED;               // the pipeline handles the flat layout only
   const int per = 32 / bits;
   const int64_t G = K / group_size;
-  if (zp_packed_host != nullptr && (G % per) != 0) return AWQK_E_UNSUPPORTED;  // row-wise zero packing
   SetDevice sd(p->device);
   if (!sd.ok) return AWQK_E_NODEVICE;
-
   const size_t esz = (dtype == AWQK_FP32) ? 4 : 2;
   const int64_t n = C * K;
+
+  if (zp_packed_host != nullptr && (G % per) != 0) {
+    // ---- row mode: packed zero points are padded per row, so chunks are whole rows and K1 is called
+    // with the row structure (it packs the zero points row-wise itself).
+    const int64_t zw = ceil_div(G, per);                       // packed zero words per row
+    int64_t rows = std::min<int64_t>((int64_t)(p->chunk_bytes / esz) / K, (int64_t)p->elems_max / K);
+    if (rows < 1) return AWQK_E_WORKSPACE;                     // one row does not fit a chunk
+    const uint8_t* src = static_cast<const uint8_t*>(w_host);
+    int i = 0;
+    for (int64_t r0 = 0; r0 < C; r0 += rows, ++i) {
+      const int b = i % awqk_pipe::kBuf;
+      const int64_t nr = std::min<int64_t>(rows, C - r0);
+      const int64_t ne = nr * K, e0 = r0 * K;
+      if (q_unpacked_host != nullptr && p->d_qu[b] == nullptr)
+        AWQK_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_qu[b]), p->elems_max * 4));
+      if (p->used[b]) AWQK_CUDA(cudaStreamWaitEvent(p->s_in, p->ev_out[b], 0));
+      AWQK_CUDA(cudaMemcpyAsync(p->d_in[b], src + (size_t)e0 * esz, (size_t)ne * esz, cudaMemcpyHostToDevice, p->s_in));
+      AWQK_CUDA(cudaEventRecord(p->ev_in[b], p->s_in));
+      AWQK_CUDA(cudaStreamWaitEvent(p->s_k, p->ev_in[b], 0));
+      const int rc = awqk_group_quant(p->d_in[b], dtype, nr, K, group_size, bits, symmetric, arith,
+                                      q_unpacked_host ? p->d_qu[b] : nullptr, q_packed_host ? p->d_qp[b] : nullptr,
+                                      p->d_sc[b], p->d_zp[b], p->d_zpp[b], nullptr, p->s_k);
+      if (rc != AWQK_OK) return rc;
+      AWQK_CUDA(cudaEventRecord(p->ev_k[b], p->s_k));
+      AWQK_CUDA(cudaStreamWaitEvent(p->s_out, p->ev_k[b], 0));
+      if (q_packed_host)
+        AWQK_CUDA(cudaMemcpyAsync(q_packed_host + e0 / per, p->d_qp[b], (size_t)(ne / per) * 4, cudaMemcpyDeviceToHost, p->s_out));
+      if (q_unpacked_host)
+        AWQK_CUDA(cudaMemcpyAsync(q_unpacked_host + e0, p->d_qu[b], (size_t)ne * 4, cudaMemcpyDeviceToHost, p->s_out));
+      AWQK_CUDA(cudaMemcpyAsync(static_cast<uint16_t*>(scales_f16_host) + r0 * G, p->d_sc[b], (size_t)(nr * G) * 2,
+                                cudaMemcpyDeviceToHost, p->s_out));
+      if (zp_host)
+        AWQK_CUDA(cudaMemcpyAsync(zp_host + r0 * G, p->d_zp[b], (size_t)(nr * G) * 4, cudaMemcpyDeviceToHost, p->s_out));
+      AWQK_CUDA(cudaMemcpyAsync(zp_packed_host + r0 * zw, p->d_zpp[b], (size_t)(nr * zw) * 4, cudaMemcpyDeviceToHost, p->s_out));
+      AWQK_CUDA(cudaEventRecord(p->ev_out[b], p->s_out));
+      p->used[b] = true;
+    }
+    return AWQK_OK;
+  }
+
+  // ---- flat mode
   // chunk = whole CTA tiles and whole packed-zero words: multiple of 8192 elements and of per*g
   int64_t chunk_elems = (int64_t)(p->chunk_bytes / esz);
   const int64_t quantum = 8192LL * ((per * group_size + 8191) / 8192);   // = 8192 for all supported (g, bits)
