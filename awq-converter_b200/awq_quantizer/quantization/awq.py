@@ -141,20 +141,33 @@ class AWQQuantizer:
         w = tensor.to(dev, non_blocking=True).contiguous()
         keep_unpacked = keep_unpacked or not pack
         out = self._quantize_device(w, pack=pack, unpacked=keep_unpacked)
+        host = self._to_host({k: v for k, v in out.items() if v is not None}, dev)
         result = {
-            "tensor_q": out["tensor_q"].cpu() if keep_unpacked else None,
-            "scales": out["scales"].cpu(),
-            "zero_points": out["zero_points"].cpu(),
+            "tensor_q": host["tensor_q"] if keep_unpacked else None,
+            "scales": host["scales"],
+            "zero_points": host["zero_points"],
             "bits": torch.tensor(self.bits, dtype=torch.int32),
             "group_size": torch.tensor(self.group_size, dtype=torch.int32),
             "symmetric": torch.tensor(self.symmetric, dtype=torch.bool),
         }
         if pack:
-            result["qweight"] = out["qweight"].cpu()
-            result["qzeros"] = out["qzeros"].cpu()
+            result["qweight"] = host["qweight"]
+            result["qzeros"] = host["qzeros"]
         if not keep_unpacked:
             del result["tensor_q"]
         return result
+
+    @staticmethod
+    def _to_host(tensors: Dict[str, torch.Tensor], dev: torch.device) -> Dict[str, torch.Tensor]:
+        """device -> host through pinned buffers (one stream sync for all of them); the results are
+        ordinary CPU tensors (awq.py:410-412 returns CPU tensors)."""
+        out = {}
+        for k, v in tensors.items():
+            h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            h.copy_(v, non_blocking=True)
+            out[k] = h
+        torch.cuda.current_stream(dev).synchronize()
+        return out
 
     def _quantize_device(self, w: torch.Tensor, *, pack: bool = False, unpacked: bool = True,
                          col_scale: Optional[torch.Tensor] = None,

@@ -83,10 +83,11 @@ def quantize_with_search(qz, tensor: torch.Tensor, activations: torch.Tensor, de
     best = int(torch.argmin(err))                      # first minimum -> ties go to the smallest alpha
     s_best = r["s_grid"][best].contiguous()
     out = qz._quantize_device(w, pack=pack, col_scale=s_best, arith="fp32")
+    out = qz._to_host(out, dev)
     result = {
-        "tensor_q": out["tensor_q"].cpu(),
-        "scales": out["scales"].cpu(),
-        "zero_points": out["zero_points"].cpu(),
+        "tensor_q": out["tensor_q"],
+        "scales": out["scales"],
+        "zero_points": out["zero_points"],
         "bits": torch.tensor(qz.bits, dtype=torch.int32),
         "group_size": torch.tensor(qz.group_size, dtype=torch.int32),
         "symmetric": torch.tensor(qz.symmetric, dtype=torch.bool),
@@ -96,8 +97,8 @@ def quantize_with_search(qz, tensor: torch.Tensor, activations: torch.Tensor, de
         "search_err": err,
     }
     if pack:
-        result["qweight"] = out["qweight"].cpu()
-        result["qzeros"] = out["qzeros"].cpu()
+        result["qweight"] = out["qweight"]
+        result["qzeros"] = out["qzeros"]
     return result
 
 

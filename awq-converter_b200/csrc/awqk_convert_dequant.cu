@@ -54,38 +54,42 @@ __global__ void bf16_to_fp16_scalar(const uint16_t* __restrict__ in, uint16_t* _
 // out = float( fp16_rn( half(q - zp) * scale ) ).  The reference multiplies an int32 tensor by a
 // 0-d fp16 tensor: torch promotes to fp16, evaluates in fp32 and rounds once (awq.py:282).
 __device__ __forceinline__ float dequant_one(int q, int zp, float scale_f) {
-  const float diff = __half2float(__int2half_rn(q - zp));   // int32 -> fp16 (RNE, overflow -> inf)
+  const int d = (int)((unsigned)q - (unsigned)zp);          // int32 wrap-around like torch's int32 subtraction
+  const float diff = __half2float(__int2half_rn(d));        // int32 -> fp16 (RNE, overflow -> inf)
   return __half2float(__float2half_rn(__fmul_rn(diff, scale_f)));
+}
+
+// fast path: K % 4 == 0 and g % 4 == 0 -> the 4 elements of a thread share one group; rows on
+// blockIdx.x, 1024-column chunks on blockIdx.y (no 64-bit divisions, 16 B in / 16 B out per thread)
+__global__ void __launch_bounds__(256)
+dequant_rows_kernel(const int32_t* __restrict__ q, const __half* __restrict__ scales, const int32_t* __restrict__ zp,
+                    int64_t K, int g, int64_t G, float* __restrict__ out) {
+  const int64_t row = blockIdx.x;
+  const uint32_t k0 = (blockIdx.y * 256u + threadIdx.x) * 4u;
+  if (k0 >= K) return;
+  const int64_t base = row * K + k0;
+  const int64_t gi = row * G + k0 / (uint32_t)g;
+  const uint4 qv = ld_stream16(q + base);
+  const int z = __ldg(zp + gi);
+  const float sc = __half2float(__ldg(scales + gi));
+  uint4 o;
+  o.x = __float_as_uint(dequant_one((int)qv.x, z, sc));
+  o.y = __float_as_uint(dequant_one((int)qv.y, z, sc));
+  o.z = __float_as_uint(dequant_one((int)qv.z, z, sc));
+  o.w = __float_as_uint(dequant_one((int)qv.w, z, sc));
+  st_stream16(out + base, o);
 }
 
 __global__ void __launch_bounds__(256)
 dequant_kernel(const int32_t* __restrict__ q, const __half* __restrict__ scales,
                const int32_t* __restrict__ zp, int64_t C, int64_t K, int g, int64_t G,
                float* __restrict__ out) {
-  // one thread per 4 consecutive elements of a row (K need not be a multiple of 4: tail scalar)
-  const int64_t vec_per_row = ceil_div(K, 4);
+  // generic: one thread per element
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= C * vec_per_row) return;
-  const int64_t row = idx / vec_per_row;
-  const int64_t k0 = (idx % vec_per_row) * 4;
-  const int64_t base = row * K + k0;
-  const bool full = (k0 + 4 <= K) && ((K & 3) == 0);
-  if (full) {
-    const int4 qv = *reinterpret_cast<const int4*>(q + base);
-    const int qs[4] = {qv.x, qv.y, qv.z, qv.w};
-    float o[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int64_t gi = row * G + (k0 + i) / g;
-      o[i] = dequant_one(qs[i], zp[gi], __half2float(scales[gi]));
-    }
-    *reinterpret_cast<float4*>(out + base) = make_float4(o[0], o[1], o[2], o[3]);
-  } else {
-    for (int i = 0; i < 4 && k0 + i < K; ++i) {
-      const int64_t gi = row * G + (k0 + i) / g;
-      out[base + i] = dequant_one(q[base + i], zp[gi], __half2float(scales[gi]));
-    }
-  }
+  if (idx >= C * K) return;
+  const int64_t row = idx / K, k = idx % K;
+  const int64_t gi = row * G + k / g;
+  out[idx] = dequant_one(q[idx], zp[gi], __half2float(scales[gi]));
 }
 
 __global__ void __launch_bounds__(256)
@@ -144,11 +148,17 @@ extern "C" int awqk_dequant(const int32_t* q_unpacked, const void* scales_f16, c
   DeviceGuard guard(q_unpacked);
   if (guard.status != AWQK_OK) return guard.status;
   const int64_t G = ceil_div(K, group_size);
-  const int64_t threads = C * ceil_div(K, 4);
-  const int64_t ctas = ceil_div(threads, 256);
-  if (ctas > 0x7FFFFFFFLL) return AWQK_E_BADARG;
-  dequant_kernel<<<(unsigned)ctas, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      q_unpacked, reinterpret_cast<const __half*>(scales_f16), zp, C, K, group_size, G, out);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((K % 4) == 0 && (group_size % 4) == 0 && C <= 0x7FFFFFFFLL && ceil_div(K, 1024) <= 65535 && K < (1LL << 32)) {
+    dim3 grid((unsigned)C, (unsigned)ceil_div(K, 1024));
+    dequant_rows_kernel<<<grid, 256, 0, st>>>(q_unpacked, reinterpret_cast<const __half*>(scales_f16), zp, K, group_size,
+                                             G, out);
+  } else {
+    const int64_t ctas = ceil_div(C * K, 256);
+    if (ctas > 0x7FFFFFFFLL) return AWQK_E_BADARG;
+    dequant_kernel<<<(unsigned)ctas, 256, 0, st>>>(q_unpacked, reinterpret_cast<const __half*>(scales_f16), zp, C, K,
+                                                  group_size, G, out);
+  }
   AWQK_CUDA(cudaGetLastError());
   return AWQK_OK;
 }

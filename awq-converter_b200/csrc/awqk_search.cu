@@ -267,7 +267,6 @@ fakequant_delta_v2(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
   r_grid += (int64_t)a_begin * K;
   dw += (int64_t)a_begin * C * K;
   __shared__ __align__(16) float sm_s[2][1024];
-  __shared__ __align__(16) float sm_r[2][1024];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.y * 8 + warp;
   const int64_t col0 = (int64_t)blockIdx.x * 1024;
@@ -293,21 +292,15 @@ fakequant_delta_v2(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
 
   __nv_bfloat16* out = dw + row * K + col;
   const int64_t plane = C * K;
-  float4 ns = make_float4(1.f, 1.f, 1.f, 1.f), nr = ns;
-  if (gvalid) {
-    ns = __ldg(reinterpret_cast<const float4*>(s_grid + gcol));
-    nr = __ldg(reinterpret_cast<const float4*>(r_grid + gcol));
-  }
+  float4 ns = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (gvalid) ns = __ldg(reinterpret_cast<const float4*>(s_grid + gcol));
 #pragma unroll 1
   for (int a = 0; a < n_s; ++a) {
     const int buf = a & 1;
     *reinterpret_cast<float4*>(&sm_s[buf][st_off]) = ns;
-    *reinterpret_cast<float4*>(&sm_r[buf][st_off]) = nr;
     __syncthreads();                                  // slab a visible; buffer buf^1 is free again after this point
-    if (a + 1 < n_s && gvalid) {                      // prefetch the next alpha's slab while computing this one
+    if (a + 1 < n_s && gvalid)                        // prefetch the next alpha's slab while computing this one
       ns = __ldg(reinterpret_cast<const float4*>(s_grid + (int64_t)(a + 1) * K + gcol));
-      nr = __ldg(reinterpret_cast<const float4*>(r_grid + (int64_t)(a + 1) * K + gcol));
-    }
     float2 sv[16], x[16];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -336,11 +329,12 @@ fakequant_delta_v2(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
       const float2 sc2 = make_float2(fg.scale, fg.scale);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float4 rr = *reinterpret_cast<const float4*>(&sm_r[buf][ld_off[c]]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int i = 2 * c + h;
-          const float2 rs = h ? make_float2(rr.z, rr.w) : make_float2(rr.x, rr.y);
+          // 1/s on the fly (MUFU + one Newton step): trades two shared-memory slabs for ALU work --
+          // the kernel is L1/shared wavefront bound, not issue bound
+          const float2 rs = make_float2(refined_rcp(sv[i].x), refined_rcp(sv[i].y));
           const float2 q0 = __fmul2_rn(x[i], r2);
           const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x[i]), r2, q0);          // x / scale, exact
           float2 v = __fadd2_rn(q, zp2);
@@ -821,12 +815,12 @@ extern "C" int awqk_alpha_grid(const double* colsum, int64_t T, int64_t K, int n
 template <typename T>
 static int launch_delta_v2(const T* w, int64_t C, int64_t K, int g, int bits, bool sym, const float* s, float* r,
                            int n_s, __nv_bfloat16* dw, cudaStream_t st) {
-  const int64_t ns = (int64_t)n_s * K;
-  rcp_grid_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(s, ns, r);
   // default: v2 (shared-memory slab; 1.6 TB/s written).  AWQK_DELTA_V3=1 selects the register-slab
   // variant (no shared memory, slower stand-alone: 1.3 TB/s) for A/B measurements.
   static const bool use_v3 = []() { const char* e = getenv("AWQK_DELTA_V3"); return e && e[0] == '1'; }();
   if (use_v3) {
+    const int64_t ns = (int64_t)n_s * K;
+    rcp_grid_kernel<<<(unsigned)ceil_div(ns, 256), 256, 0, st>>>(s, ns, r);
     const int z = std::min(n_s, 4);
     const int64_t slabs = ceil_div(K, 1024);
     // rows per warp: amortise the slab loads (>= 8 rows) but keep >= ~4 CTAs per SM in flight

@@ -329,3 +329,25 @@ def test_pipe_c_abi_unpacked_and_errors(native_lib, cuda_device):
                                                sc.data_ptr(), None, None) == -4
     finally:
         native_lib.awqk_pipe_destroy(h)
+
+
+@pytest.mark.parametrize("bits,g", [(4, 32), (4, 64), (8, 128), (8, 32)])
+def test_model_arena_other_bits_and_groups(native_lib, cuda_device, bits, g):
+    shapes = {"a": (64, 2048), "b": (16, 4096), "bias": (2048,), "rowmode": (48, 3 * g)}
+    tensors = {n: datagen.weights(s, "bf16", datagen.seed_of("arena2", n, bits, g)) for n, s in shapes.items()}
+    tensors["h"] = datagen.weights((32, 1024), "fp16", 5)
+    qz = mk(bits=bits, group_size=g, symmetric=False)
+    out = qz.quantize_model(tensors, pack=True, chunk_bytes=1 << 16)
+    for n, t in tensors.items():
+        want = O.pack_result(O.group_quant_vec(t, bits, g, False, True))
+        for k in ("qweight", "qzeros", "scales"):
+            assert_same(out[n][k], want[k], f"{n}/{k}/b{bits}/g{g}")
+
+
+def test_dequant_paths(native_lib, cuda_device):
+    """row-structured fast path (K % 4 == 0, g % 4 == 0) and the generic element path"""
+    for shape, g in (((64, 1024), 128), ((3, 4100), 100), ((5, 1030), 128), ((2, 3, 512), 64), ((7, 129), 7)):
+        w = datagen.weights(shape, "bf16", datagen.seed_of("dq", shape, g), offset=0.05)
+        qz = mk(group_size=g, symmetric=False)
+        r = qz.quantize(w)
+        assert_same(qz.dequantize(r), O.dequant_vec(r), f"{shape}/g{g}")
