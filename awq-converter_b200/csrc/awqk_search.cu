@@ -374,6 +374,155 @@ fakequant_delta_v2(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
   }
 }
 
+// ---- v4: same scheme as v2 with 16 elements per thread (a group of 128 = 8 lanes): half the
+// per-thread state -> <= 80 registers -> 3 CTAs (24 warps) per SM hide the per-alpha barrier and the
+// serial group-parameter chain.  CTA = 4 rows x 1024 columns (warps 2r, 2r+1 = the two halves of row r).
+template <typename T>
+__device__ __forceinline__ void load16(const T* p, float2 (&f)[8]);
+template <>
+__device__ __forceinline__ void load16<__nv_bfloat16>(const __nv_bfloat16* p, float2 (&f)[8]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p) + c);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      f[4 * c + i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+  }
+}
+template <>
+__device__ __forceinline__ void load16<__half>(const __half* p, float2 (&f)[8]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p) + c);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[4 * c + i] = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+  }
+}
+template <>
+__device__ __forceinline__ void load16<float>(const float* p, float2 (&f)[8]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(p) + c);
+    f[2 * c] = make_float2(r.x, r.y);
+    f[2 * c + 1] = make_float2(r.z, r.w);
+  }
+}
+
+template <typename T, int G, int BITS>
+__global__ void __launch_bounds__(256, 3)
+fakequant_delta_v4(const T* __restrict__ w, int64_t C, int64_t K, bool sym, const float* __restrict__ s_grid,
+                   int n_s_total, __nv_bfloat16* __restrict__ dw) {
+  constexpr int LPG = G / 16;
+  const int per_z = (n_s_total + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int a_begin = (int)blockIdx.z * per_z;
+  const int n_s = min(per_z, n_s_total - a_begin);
+  if (n_s <= 0) return;
+  s_grid += (int64_t)a_begin * K;
+  dw += (int64_t)a_begin * C * K;
+  __shared__ __align__(16) float sm_s[2][1024];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.y * 4 + (warp >> 1);
+  const int64_t col0 = (int64_t)blockIdx.x * 1024;
+  const int64_t col = col0 + (warp & 1) * 512 + lane * 16;
+  const bool valid = row < C && col < K;
+  const float qmin = sym ? -(float)(1 << (BITS - 1)) : 0.0f;
+  const float qmax = sym ? (float)((1 << (BITS - 1)) - 1) : (float)((1 << BITS) - 1);
+  const float2 magic2 = make_float2(12582912.0f, 12582912.0f), nmagic2 = make_float2(-12582912.0f, -12582912.0f);
+  float2 wv[8];
+  if (valid) load16<T>(w + row * K + col, wv);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[i] = make_float2(0.0f, 0.0f);
+  }
+  // staging: thread t fetches floats [4t, 4t+4): 64-byte row t/4 (= half * 32 + lane), chunk t % 4,
+  // stored at position (chunk + (lane >> 1)) & 3 -> quarter-warps read 8 distinct bank groups
+  const int t = threadIdx.x;
+  const int64_t gcol = col0 + 4 * t;
+  const bool gvalid = gcol < K;
+  const int st_off = (t >> 2) * 16 + ((((t & 3) + (((t >> 2) & 31) >> 1)) & 3) << 2);
+  int ld_off[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) ld_off[c] = ((warp & 1) * 32 + lane) * 16 + (((c + (lane >> 1)) & 3) << 2);
+
+  __nv_bfloat16* out = dw + row * K + col;
+  const int64_t plane = C * K;
+  float4 ns = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (gvalid) ns = __ldg(reinterpret_cast<const float4*>(s_grid + gcol));
+#pragma unroll 1
+  for (int a = 0; a < n_s; ++a) {
+    const int buf = a & 1;
+    *reinterpret_cast<float4*>(&sm_s[buf][st_off]) = ns;
+    __syncthreads();
+    if (a + 1 < n_s && gvalid) ns = __ldg(reinterpret_cast<const float4*>(s_grid + (int64_t)(a + 1) * K + gcol));
+    float2 sv[8], x[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(&sm_s[buf][ld_off[c]]);
+      sv[2 * c] = make_float2(v.x, v.y);
+      sv[2 * c + 1] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __fmul2_rn(wv[i], sv[i]);                   // Ws = W * s
+    float mn = dq_fmin_nan(x[0].x, x[0].y), mx = dq_fmax_nan(x[0].x, x[0].y);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      mn = dq_fmin_nan(mn, dq_fmin_nan(x[i].x, x[i].y));
+      mx = dq_fmax_nan(mx, dq_fmax_nan(x[i].x, x[i].y));
+    }
+#pragma unroll
+    for (int m = 1; m < LPG; m <<= 1) {
+      mn = dq_fmin_nan(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, m));
+      mx = dq_fmax_nan(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
+    }
+    const FastGroup fg = group_params_fast<AR_F32, BITS>(mn, mx, sym, qmin, qmax);
+    uint32_t o[8];
+    if (fg.ok) {
+      const float2 r2 = make_float2(fg.rcp, fg.rcp), ns2 = make_float2(-fg.scale, -fg.scale);
+      const float2 zp2 = make_float2(fg.zp, fg.zp), nzp2 = make_float2(-fg.zp, -fg.zp);
+      const float2 sc2 = make_float2(fg.scale, fg.scale);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 rs = make_float2(refined_rcp(sv[i].x), refined_rcp(sv[i].y));
+        const float2 q0 = __fmul2_rn(x[i], r2);
+        const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x[i]), r2, q0);            // x / scale, exact
+        float2 v = __fadd2_rn(q, zp2);
+        v.x = fminf(fmaxf(v.x, qmin), qmax);
+        v.y = fminf(fmaxf(v.y, qmin), qmax);
+        const float2 qf = __fadd2_rn(__fadd2_rn(v, magic2), nmagic2);              // rint (half-to-even)
+        const float2 d = __fmul2_rn(__fadd2_rn(qf, nzp2), sc2);                    // (q - zp) * scale
+        const float2 h0 = __fmul2_rn(d, rs);
+        const float2 nsv = make_float2(-sv[i].x, -sv[i].y);
+        const float2 what = __ffma2_rn(__ffma2_rn(nsv, h0, d), rs, h0);            // deq / s, exact
+        const float2 dl = __fadd2_rn(wv[i], make_float2(-what.x, -what.y));        // W - W^
+        const __nv_bfloat162 b = __float22bfloat162_rn(dl);
+        o[i] = *reinterpret_cast<const uint32_t*>(&b);
+      }
+    } else {
+      const GroupParams gp = group_params<AR_F32>(mn, mx, sym, qmin, qmax);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float d2[2];
+        const float xs[2] = {x[i].x, x[i].y}, ss[2] = {sv[i].x, sv[i].y}, ww[2] = {wv[i].x, wv[i].y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float r = rintf(__fadd_rn(__fdiv_rn(xs[h], gp.scale), gp.zp));
+          const float qf = (r != r) ? r : fminf(fmaxf(r, qmin), qmax);
+          d2[h] = __fsub_rn(ww[h], __fdiv_rn(__fmul_rn(__fsub_rn(qf, gp.zp), gp.scale), ss[h]));
+        }
+        const __nv_bfloat162 b = __floats2bfloat162_rn(d2[0], d2[1]);
+        o[i] = *reinterpret_cast<const uint32_t*>(&b);
+      }
+    }
+    if (valid) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (int64_t)a * plane);
+      st_stream16(dst, make_uint4(o[0], o[1], o[2], o[3]));
+      st_stream16(dst + 1, make_uint4(o[4], o[5], o[6], o[7]));
+    }
+  }
+}
+
 // 32 consecutive elements of a W row, kept in the narrowest register form
 template <typename T>
 struct Row32;
@@ -835,6 +984,22 @@ static int launch_delta_v2(const T* w, int64_t C, int64_t K, int g, int bits, bo
       if (g == 32) AWQK_DELTA3(32, 8); else if (g == 64) AWQK_DELTA3(64, 8); else AWQK_DELTA3(128, 8);
     }
 #undef AWQK_DELTA3
+    AWQK_CUDA(cudaGetLastError());
+    return AWQK_OK;
+  }
+  static const bool use_v2 = []() { const char* e = getenv("AWQK_DELTA_V2"); return e && e[0] == '1'; }();
+  if (!use_v2 && ceil_div(C, 4) <= 65535) {      // default: v4 (16 elements per thread, 3 CTAs/SM)
+    // alpha slices: enough CTAs for ~4 waves of 3 x 148, but no more (each slice re-reads its W rows)
+    const int64_t base_ctas = ceil_div(K, 1024) * ceil_div(C, 4);
+    const int z = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_s, 4), ceil_div(1800, base_ctas)));
+    dim3 g4((unsigned)ceil_div(K, 1024), (unsigned)ceil_div(C, 4), (unsigned)z);
+#define AWQK_DELTA4(GG, BB) fakequant_delta_v4<T, GG, BB><<<g4, 256, 0, st>>>(w, C, K, sym, s, n_s, dw)
+    if (bits == 4) {
+      if (g == 32) AWQK_DELTA4(32, 4); else if (g == 64) AWQK_DELTA4(64, 4); else AWQK_DELTA4(128, 4);
+    } else {
+      if (g == 32) AWQK_DELTA4(32, 8); else if (g == 64) AWQK_DELTA4(64, 8); else AWQK_DELTA4(128, 8);
+    }
+#undef AWQK_DELTA4
     AWQK_CUDA(cudaGetLastError());
     return AWQK_OK;
   }
