@@ -294,7 +294,7 @@ def bench_leg(args, dev, world: int, rank: int, tf_peak: float, peak_kind: str):
         "s_per_model": ms * 1e-3, "tokens": T, "n_grid": n_grid, "linears_per_rank": len(mine),
         "tflops_executed": flops / (ms * 1e-3) / 1e12,
         "flops_executed": flops, "flops_survey_formula": flops * (n_grid + 1) / n_grid,
-        "roofline": {"bound": "tensor", "kernel": "sqerr_gemm_kernel (tcgen05, K2)", "achieved": gemm_tf, "peak": tf_peak,
+        "roofline": {"bound": "tensor", "kernel": "sqerr_gemm2_kernel (tcgen05 cta_group::2, K2)", "achieved": gemm_tf, "peak": tf_peak,
                      "unit": "TFLOP/s", "frac": gemm_tf / tf_peak, "peak_source": peak_kind + " (sustained bf16)",
                      "shape": f"T={T} C={C} K={K} n_s={n_s}", "ms_per_launch": gemm_ms, "traffic": None},
     }

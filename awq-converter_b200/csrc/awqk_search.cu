@@ -923,6 +923,10 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// awqk_search_gemm2.cu: CTA-pair (cta_group::2) version of the same GEMM
+int launch_sqerr_gemm2(const void* x_bf16, const void* dw_bf16, int64_t T, int64_t C, int64_t K, int n_s, double* err,
+                       cudaStream_t st);
+
 }  // namespace awqk
 
 using namespace awqk;
@@ -1084,6 +1088,12 @@ extern "C" int awqk_sqerr_gemm(const void* x_bf16, const void* dw_bf16, int64_t 
   if (T > 0x7FFFFFFF || C > 0x7FFFFFFF || K > 0x7FFFFFFF) return AWQK_E_BADARG;
   DeviceGuard guard(x_bf16);
   if (guard.status != AWQK_OK) return guard.status;
+  {
+    // default: the CTA-pair kernel (tcgen05 cta_group::2, awqk_search_gemm2.cu); AWQK_GEMM_2CTA=0 selects
+    // the single-CTA kernel below (kept for A/B measurements; same results)
+    static const int two_cta = []() { const char* e = getenv("AWQK_GEMM_2CTA"); return (e && e[0] == '0') ? 0 : 1; }();
+    if (two_cta) return launch_sqerr_gemm2(x_bf16, dw_bf16, T, C, K, n_s, err, reinterpret_cast<cudaStream_t>(stream));
+  }
   EncodeTiledFn encode = get_encode_fn();
   if (encode == nullptr) return AWQK_E_NODEVICE;
 
