@@ -351,3 +351,89 @@ def test_dequant_paths(native_lib, cuda_device):
         qz = mk(group_size=g, symmetric=False)
         r = qz.quantize(w)
         assert_same(qz.dequantize(r), O.dequant_vec(r), f"{shape}/g{g}")
+
+
+def test_more_than_2_31_elements(native_lib, cuda_device):
+    """64-bit indexing: a 2.7e9-element bf16 tensor through the flat TMA kernel (row-slice parity vs the
+    oracle, pack/unpack identity by blocks)"""
+    dev = cuda_device
+    C, K, g = 40960, 65536, 128
+    assert C * K > 2 ** 31
+    gen = torch.Generator(device=dev).manual_seed(7)
+    w = torch.empty((C, K), dtype=torch.bfloat16, device=dev)
+    for r0 in range(0, C, 4096):                                   # generate in blocks (fp32 scratch stays small)
+        w[r0:r0 + 4096] = (torch.randn((4096, K), generator=gen, device=dev) * 0.02).to(torch.bfloat16)
+    qz = mk(symmetric=False)
+    full = qz._quantize_device(w, pack=True, unpacked=False)
+    rows = torch.tensor([0, 1, 32767, 32768, 32769, 40959], device=dev)    # around the 2^31-element boundary
+    sub = w[rows].cpu()
+    want = O.pack_result(O.group_quant_vec(sub, 4, g, False, True))
+    for k in ("scales", "zero_points", "qweight", "qzeros"):
+        assert_same(full[k][rows].cpu(), want[k], k)
+    # a second, independent quantization of the upper half must equal the slices of the full result
+    part = qz._quantize_device(w[32768:].contiguous(), pack=True, unpacked=False)
+    assert torch.equal(part["qweight"], full["qweight"][32768:])
+    assert torch.equal(part["scales"], full["scales"][32768:]) and torch.equal(part["qzeros"], full["qzeros"][32768:])
+    del w, full, part
+    torch.cuda.empty_cache()
+
+
+def _guarded(nbytes, dev):
+    """(buffer, view): `view` is nbytes in the middle of a buffer whose 4 KiB borders hold a canary"""
+    pad = 4096
+    buf = torch.full((nbytes + 2 * pad,), 0xA5, dtype=torch.uint8, device=dev)
+    return buf, buf[pad:pad + nbytes]
+
+
+def _canaries_intact(buf, nbytes):
+    pad = 4096
+    return bool((buf[:pad] == 0xA5).all()) and bool((buf[pad + nbytes:] == 0xA5).all())
+
+
+def test_no_out_of_bounds_writes(native_lib, cuda_device):
+    """compute-sanitizer is closed on this pool: guard every output buffer with canaries instead
+    (partial CTA tiles, row mode, generic path, convert, de-quantizer, fake-quant delta)"""
+    from awq_quantizer import _native as N
+    dev = cuda_device
+    L = native_lib
+    for (C, K), g, bits in (((72, 1152), 128, 4), ((9, 1024), 32, 4), ((5, 640), 64, 8), ((7, 300), 128, 4), ((1, 128), 128, 4)):
+        w = datagen.weights((C, K), "bf16", datagen.seed_of("oob", C, K)).to(dev)
+        G = -(-K // g)
+        per = 32 // bits
+        sizes = {"q": C * K * 4, "qp": C * (-(-K // per)) * 4, "s": C * G * 2, "z": C * G * 4, "zq": C * (-(-G // per)) * 4}
+        bufs = {k: _guarded(v, dev) for k, v in sizes.items()}
+        for unpacked in (True, False):
+            rc = L.awqk_group_quant(w.data_ptr(), N.BF16, C, K, g, bits, 0, N.ARITH_NATIVE,
+                                    bufs["q"][1].data_ptr() if unpacked else None, bufs["qp"][1].data_ptr(),
+                                    bufs["s"][1].data_ptr(), bufs["z"][1].data_ptr(), bufs["zq"][1].data_ptr(), None, None)
+            assert rc == 0
+            torch.cuda.synchronize()
+            for k, (b, _) in bufs.items():
+                assert _canaries_intact(b, sizes[k]), (C, K, g, bits, unpacked, k)
+        want = O.pack_result(O.group_quant_vec(w.cpu(), bits, g, False, True))
+        got_qp = bufs["qp"][1].view(torch.int32).reshape(C, -1).cpu()
+        assert_same(got_qp, want["qweight"], f"{C}x{K}")
+        # dequant + convert
+        out_b, out_v = _guarded(C * K * 4, dev)
+        assert L.awqk_dequant(bufs["q"][1].data_ptr(), bufs["s"][1].data_ptr(), bufs["z"][1].data_ptr(), C, K, g,
+                              out_v.data_ptr(), None) == 0
+        h_b, h_v = _guarded(C * K * 2, dev)
+        assert L.awqk_bf16_to_fp16(w.data_ptr(), h_v.data_ptr(), C * K, None) == 0
+        torch.cuda.synchronize()
+        assert _canaries_intact(out_b, C * K * 4) and _canaries_intact(h_b, C * K * 2)
+    # fake-quant delta (both kernels) and the GEMM's err vector
+    C, K, n = 37, 1280, 3
+    w = datagen.weights((C, K), "bf16", 3).to(dev)
+    s = (torch.rand((n, K), device=dev) + 0.5)
+    rws = torch.empty_like(s)
+    for ws in (None, rws.data_ptr()):
+        dw_b, dw_v = _guarded(n * C * K * 2, dev)
+        assert L.awqk_fakequant_delta(w.data_ptr(), N.BF16, C, K, 128, 4, 0, s.data_ptr(), n, dw_v.data_ptr(), ws, None) == 0
+        torch.cuda.synchronize()
+        assert _canaries_intact(dw_b, n * C * K * 2)
+    x = datagen.activations(70, K, "bf16", 5).to(dev)
+    e_b, e_v = _guarded(n * 8, dev)
+    e_v.zero_()
+    assert L.awqk_sqerr_gemm(x.data_ptr(), dw_v.data_ptr(), 70, C, K, n, e_v.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert _canaries_intact(e_b, n * 8) and float(e_v.view(torch.float64).min()) > 0
