@@ -134,6 +134,17 @@ AWQK_API int awqk_sqerr_gemm(const void* x_bf16, const void* dw_bf16, int64_t T,
                     int n_s, double* err, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Interop export: K1's packed int4 result -> the AutoAWQ / vLLM "GEMM" checkpoint layout.
+ *   in : q_packed [C, K/8] (K1 packing), zp int32 [C, G], scales fp16 [C, G]
+ *   out: qweight [K, C/8] with the 0,2,4,6,1,3,5,7 nibble interleave along C, qzeros [G, C/8] (same
+ *        packing of zp - qmin), scales fp16 [G, C].   Requires C % 8 == 0 and K % 8 == 0.
+ * The closest the reference gets is its non-functional examples/load_quantized_model.py.
+ * ------------------------------------------------------------------------------------- */
+AWQK_API int awqk_export_autoawq(const uint32_t* q_packed, const int32_t* zp, const void* scales_f16, int64_t C,
+                        int64_t K, int64_t G, int symmetric, uint32_t* qweight_out, uint32_t* qzeros_out,
+                        void* scales_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Host-buffer pipeline (the e2e path): quantize+pack a host-resident weight through chunked,
  * double-buffered H2D -> K1 -> D2H on private streams.  Host buffers should be pinned
  * (cudaHostAlloc / torch pin_memory) for the copies to overlap.

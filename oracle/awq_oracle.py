@@ -290,6 +290,43 @@ def pack_result(qd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
 
 
 # --------------------------------------------------------------------------
+# Interop layout -- PARITY UNPINNED (the reference has no exporter; this is the
+# public AutoAWQ "GEMM" checkpoint layout, stated from general knowledge)
+# --------------------------------------------------------------------------
+AWQ_ORDER = (0, 2, 4, 6, 1, 3, 5, 7)
+
+
+def _pack_awq(mat: torch.Tensor) -> torch.Tensor:
+    """mat int [R, C] of 4-bit values -> int32 [R, C/8]; nibble i of word j = mat[:, 8j + AWQ_ORDER[i]]"""
+    R, Cn = mat.shape
+    m = mat.to(torch.int64).reshape(R, Cn // 8, 8)
+    word = torch.zeros((R, Cn // 8), dtype=torch.int64)
+    for i, o in enumerate(AWQ_ORDER):
+        word |= (m[:, :, o] & 15) << (4 * i)
+    word = torch.where(word >= 2 ** 31, word - 2 ** 32, word)
+    return word.to(torch.int32)
+
+
+def to_autoawq_gemm(qd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """quantize() dict of a 2-D asymmetric int4 weight [C, K] -> {'qweight' [K, C/8], 'qzeros' [G, C/8],
+    'scales' [G, C]}: w[c, k] ~ (q - z) * s with q, z in [0, 15]."""
+    qmin, _ = qrange(int(qd["bits"].item()), bool(qd["symmetric"].item()))
+    q = qd["tensor_q"] - qmin
+    z = qd["zero_points"] - qmin
+    return {"qweight": _pack_awq(q.t().contiguous()), "qzeros": _pack_awq(z.t().contiguous()),
+            "scales": qd["scales"].t().contiguous()}
+
+
+def from_autoawq_gemm(qweight: torch.Tensor, n_out: int) -> torch.Tensor:
+    """inverse of _pack_awq: int32 [R, C/8] -> int32 [R, C]"""
+    w = qweight.to(torch.int64) & 0xFFFFFFFF
+    out = torch.zeros((qweight.shape[0], n_out // 8, 8), dtype=torch.int64)
+    for i, o in enumerate(AWQ_ORDER):
+        out[:, :, o] = (w >> (4 * i)) & 15
+    return out.reshape(qweight.shape[0], n_out).to(torch.int32)
+
+
+# --------------------------------------------------------------------------
 # Activation-aware alpha search -- PARITY UNPINNED (absent from the reference;
 # public AWQ algorithm, arXiv 2306.00978, frozen here as the definition)
 # --------------------------------------------------------------------------

@@ -437,3 +437,17 @@ def test_no_out_of_bounds_writes(native_lib, cuda_device):
     assert L.awqk_sqerr_gemm(x.data_ptr(), dw_v.data_ptr(), 70, C, K, n, e_v.data_ptr(), None) == 0
     torch.cuda.synchronize()
     assert _canaries_intact(e_b, n * 8) and float(e_v.view(torch.float64).min()) > 0
+
+
+@pytest.mark.parametrize("shape", [(64, 256), (136, 1024), (8, 8 * 128), (200, 520)])
+def test_autoawq_export_vs_oracle(native_lib, cuda_device, shape):
+    from awq_quantizer.quantization.export import to_autoawq_gemm
+    w = datagen.weights(shape, "bf16", datagen.seed_of("awq", shape))
+    for sym in (False, True):
+        r = mk(symmetric=sym).quantize(w, pack=True)
+        got = to_autoawq_gemm(r, device="cuda:0")
+        want = O.to_autoawq_gemm(O.group_quant_vec(w, 4, 128, sym, True))
+        for k in ("qweight", "qzeros", "scales"):
+            assert_same(got[k], want[k], f"{shape}/{sym}/{k}")
+    with pytest.raises(ValueError):
+        to_autoawq_gemm(mk(bits=8).quantize(w, pack=True))

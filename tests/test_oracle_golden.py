@@ -184,3 +184,16 @@ def test_c_oracle_matches_goldens_and_python_oracle(small, special):
                                    O.group_quant_vec(w, 4, 128, sym, True, arith="fp32"), key + "/fp32")
     codes = torch.randint(0, 16, (7, 100), dtype=torch.int32)
     assert torch.equal(CO.pack_rows(codes, 0, 4), O.pack_rows_u32(codes, 0, 4))
+
+
+def test_autoawq_layout_roundtrip():
+    w = datagen.weights((64, 256), "bf16", 5)
+    r = O.group_quant_vec(w, 4, 128, False, True)
+    a = O.to_autoawq_gemm(r)
+    assert a["qweight"].shape == (256, 8) and a["qzeros"].shape == (2, 8) and a["scales"].shape == (2, 64)
+    assert torch.equal(O.from_autoawq_gemm(a["qweight"], 64).t(), r["tensor_q"])
+    assert torch.equal(O.from_autoawq_gemm(a["qzeros"], 64).t(), r["zero_points"])
+    # first word of row 0 holds output channels 0,2,4,6,1,3,5,7 of input feature 0
+    q = r["tensor_q"][:, 0]
+    want = sum(int(q[o]) << (4 * i) for i, o in enumerate(O.AWQ_ORDER))
+    assert (int(a["qweight"][0, 0]) & 0xFFFFFFFF) == want
