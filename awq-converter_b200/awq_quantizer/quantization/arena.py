@@ -104,46 +104,53 @@ class _PipeHandle:
 
 def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: bool, arith: str,
                    device: torch.device, chunk_bytes: int = 32 << 20, want_zero_points: bool = False,
-                   out: Optional[dict] = None, sync: bool = True) -> Dict[str, Dict[str, torch.Tensor]]:
-    """Quantize+pack every tensor of ``arena``.  Returns name -> {'qweight', 'qzeros', 'scales'
-    (+ 'zero_points'), 'bits', 'group_size', 'symmetric'}; the tensors are views of pinned host output
-    arenas (``out`` may carry those arenas across calls to avoid re-allocating them)."""
+                   out: Optional[dict] = None, sync: bool = True, packed: bool = True,
+                   unpacked: bool = False) -> Dict[str, Dict[str, torch.Tensor]]:
+    """Quantize every tensor of ``arena`` through the chunked H2D -> K1 -> D2H pipeline.
+
+    ``packed``   -> 'qweight' / 'qzeros' (+ 'scales'), ``unpacked`` -> the reference's 'tensor_q' int32 /
+    'zero_points' int32 (+ 'scales').  The tensors are views of pinned host output arenas (``out`` may
+    carry those arenas across calls to avoid re-allocating them)."""
     per = 32 // bits
     L = N.lib()
     pipe = _PipeHandle.get(device.index if device.index is not None else torch.cuda.current_device(), chunk_bytes)
     results: Dict[str, Dict[str, torch.Tensor]] = {}
     outs = out if out is not None else {}
+    want_z = want_zero_points or unpacked
     for dtype, buf in arena.buffers.items():
         n = buf.numel()
-        key = (dtype, n, bits, group_size, want_zero_points)
+        key = (dtype, n, bits, group_size, want_z, packed, unpacked)
         if key not in outs:
             pin = torch.cuda.is_available()
             outs[key] = {
-                "q": torch.empty(n // per, dtype=torch.int32, pin_memory=pin),
+                "q": torch.empty(n // per, dtype=torch.int32, pin_memory=pin) if packed else None,
                 "s": torch.empty(n // group_size, dtype=torch.float16, pin_memory=pin),
-                "zq": torch.empty(n // group_size // per, dtype=torch.int32, pin_memory=pin),
-                "z": torch.empty(n // group_size, dtype=torch.int32, pin_memory=pin) if want_zero_points else None,
+                "zq": torch.empty(n // group_size // per, dtype=torch.int32, pin_memory=pin) if packed else None,
+                "z": torch.empty(n // group_size, dtype=torch.int32, pin_memory=pin) if want_z else None,
+                "tq": torch.empty(n, dtype=torch.int32, pin_memory=pin) if unpacked else None,
             }
         o = outs[key]
         N.check(L.awqk_pipe_quant_host(pipe, buf.data_ptr(), N.dtype_code(dtype), 1, n, group_size, bits,
                                        int(symmetric), N.ARITH_FP32 if arith == "fp32" else N.ARITH_NATIVE,
-                                       None, o["q"].data_ptr(), o["s"].data_ptr(), N.ptr(o["z"]),
-                                       o["zq"].data_ptr()), "awqk_pipe_quant_host")
+                                       N.ptr(o["tq"]), N.ptr(o["q"]), o["s"].data_ptr(), N.ptr(o["z"]),
+                                       N.ptr(o["zq"])), "awqk_pipe_quant_host")
         for name, off, numel in arena.layout[dtype]:
             shape = arena.specs[name][0]
             rows = 1 if len(shape) <= 1 else shape[0]
             k = numel // rows
             g = k // group_size
-            r = {
-                "qweight": o["q"][off // per:(off + numel) // per].view(rows, k // per),
-                "qzeros": o["zq"][off // group_size // per:(off + numel) // group_size // per].view(rows, g // per),
-                "scales": o["s"][off // group_size:(off + numel) // group_size].view(rows, g),
-                "bits": torch.tensor(bits, dtype=torch.int32),
-                "group_size": torch.tensor(group_size, dtype=torch.int32),
-                "symmetric": torch.tensor(symmetric, dtype=torch.bool),
-            }
-            if want_zero_points:
+            r = {}
+            if unpacked:
+                r["tensor_q"] = o["tq"][off:off + numel].view(shape)
+            r["scales"] = o["s"][off // group_size:(off + numel) // group_size].view(rows, g)
+            if want_z:
                 r["zero_points"] = o["z"][off // group_size:(off + numel) // group_size].view(rows, g)
+            r["bits"] = torch.tensor(bits, dtype=torch.int32)
+            r["group_size"] = torch.tensor(group_size, dtype=torch.int32)
+            r["symmetric"] = torch.tensor(symmetric, dtype=torch.bool)
+            if packed:
+                r["qweight"] = o["q"][off // per:(off + numel) // per].view(rows, k // per)
+                r["qzeros"] = o["zq"][off // group_size // per:(off + numel) // group_size // per].view(rows, g // per)
             results[name] = r
     if sync:
         N.check(L.awqk_pipe_sync(pipe), "awqk_pipe_sync")

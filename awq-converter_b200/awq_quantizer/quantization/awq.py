@@ -194,16 +194,37 @@ class AWQQuantizer:
         return out
 
     # ------------------------------------------------------------------ awq.py:435-457
-    def quantize_model(self, tensors, *, pack: bool = False, chunk_bytes: int = 32 << 20):
+    def quantize_model(self, tensors, *, pack: bool = False, chunk_bytes: int = 32 << 20, pipeline: bool = True):
         """dict-in / dict-out; a tensor that raises is logged and skipped (awq.py:453-455).
 
-        ``pack=False`` (default): the reference's result layout per tensor (``tensor_q`` int32 ...).
-        ``pack=True``: packed results (``qweight`` / ``qzeros`` / ``scales``).  Every tensor whose rows
-        are whole groups goes through ONE flat arena per dtype and the chunked H2D -> K1 -> D2H
-        pipeline (quantization/arena.py); ``tensors`` may already be a ``HostArena`` (zero-copy)."""
+        ``pack=False`` (default): the reference's result layout per tensor (``tensor_q`` int32, ``scales``
+        fp16, ``zero_points`` int32 ...).  ``pack=True``: packed results (``qweight`` / ``qzeros`` /
+        ``scales``).  Either way every CPU tensor whose rows are whole groups (and, for the flat arena,
+        whole packed-zero words) goes through ONE flat arena per dtype and the chunked H2D -> K1 -> D2H
+        pipeline (quantization/arena.py) instead of a per-tensor upload / kernel / download sequence;
+        the results are then views of pinned host arenas.  ``pipeline=False`` forces the per-tensor loop.
+        ``tensors`` may already be a ``HostArena`` (zero-copy)."""
         if not pack:
-            quantized = {}
-            for name, tensor in tensors.items():
+            from .arena import HostArena, pipe_eligible, quantize_arena
+            quantized, rest = {}, tensors
+            if pipeline and self.zero_point != "percentile" and torch.cuda.is_available() and \
+                    torch.device(self.device).type == "cuda":
+                dev = self._cuda_device()
+                flat = {n: t for n, t in tensors.items()
+                        if isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.numel() >= self.group_size
+                        and pipe_eligible(tuple(t.shape), t.dtype, self.group_size, self.bits)}
+                if flat:
+                    try:
+                        res = quantize_arena(HostArena.from_tensors(flat), bits=self.bits, group_size=self.group_size,
+                                             symmetric=self.symmetric, arith=self.arith, device=dev,
+                                             chunk_bytes=chunk_bytes, packed=False, unpacked=True)
+                        for name in flat:
+                            self.logger.info(f"Successfully quantized tensor: {name}")
+                        quantized.update(res)
+                        rest = {n: t for n, t in tensors.items() if n not in flat}
+                    except Exception as e:
+                        self.logger.error(f"Pipelined quantization failed ({e}); using the per-tensor path")
+            for name, tensor in rest.items():
                 try:
                     self.logger.info(f"Quantizing tensor: {name}")
                     quantized[name] = self.quantize(tensor)
@@ -211,7 +232,7 @@ class AWQQuantizer:
                 except Exception as e:
                     self.logger.error(f"Error quantizing tensor: {name}, error: {e}")
                     continue
-            return quantized
+            return {n: quantized[n] for n in tensors if n in quantized}       # input order, like the reference
 
         from .arena import (HostArena, arena_eligible, pipe_eligible, quantize_arena, quantize_rows_pipelined,
                             sync_pipe)

@@ -451,3 +451,26 @@ def test_autoawq_export_vs_oracle(native_lib, cuda_device, shape):
             assert_same(got[k], want[k], f"{shape}/{sym}/{k}")
     with pytest.raises(ValueError):
         to_autoawq_gemm(mk(bits=8).quantize(w, pack=True))
+
+
+def test_default_quantize_model_is_pipelined_and_reference_exact(native_lib, cuda_device):
+    """quantize_model(tensors) with unchanged arguments: reference layout, bit-exact, input order kept,
+    bad tensors skipped -- now through the arena pipeline for every whole-group tensor"""
+    shapes = {"w1": (64, 1024), "odd_g": (96, 512), "bias": (1024,), "ragged": (7, 300), "tiny": (10, 10), "conv": (16, 3, 256)}
+    tensors = {n: datagen.weights(s, "bf16", datagen.seed_of("dflt", n)) for n, s in shapes.items()}
+    tensors["bad"] = torch.zeros(4, 4, dtype=torch.int64)
+    tensors["h"] = datagen.weights((8, 256), "fp16", 3)
+    for sym in (False, True):
+        qz = mk(symmetric=sym)
+        out = qz.quantize_model(tensors, chunk_bytes=1 << 16)
+        assert list(out) == [n for n in tensors if n != "bad"]
+        for n, r in out.items():
+            want = O.group_quant_vec(tensors[n], 4, 128, sym, True)
+            assert_quant_equal(r, want, n)
+            assert r["tensor_q"].shape == tensors[n].shape and r["tensor_q"].device.type == "cpu"
+            assert int(r["bits"]) == 4 and bool(r["symmetric"]) == sym
+            if r["scales"].dim() == 2:
+                assert_same(qz.dequantize(r), O.dequant_vec(want), n + "/dequant")
+        loop = qz.quantize_model(tensors, pipeline=False)
+        for n in out:
+            assert_quant_equal(out[n], loop[n], n + "/loop")
