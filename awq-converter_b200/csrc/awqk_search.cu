@@ -422,6 +422,7 @@ fakequant_delta_v4(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
   s_grid += (int64_t)a_begin * K;
   dw += (int64_t)a_begin * C * K;
   __shared__ __align__(16) float sm_s[2][1024];
+  __shared__ __align__(16) float sm_r[2][1024];   // refined 1/s, computed once per CTA (4 rows share it)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t row = (int64_t)blockIdx.y * 4 + (warp >> 1);
   const int64_t col0 = (int64_t)blockIdx.x * 1024;
@@ -454,6 +455,8 @@ fakequant_delta_v4(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
   for (int a = 0; a < n_s; ++a) {
     const int buf = a & 1;
     *reinterpret_cast<float4*>(&sm_s[buf][st_off]) = ns;
+    *reinterpret_cast<float4*>(&sm_r[buf][st_off]) =
+        make_float4(refined_rcp(ns.x), refined_rcp(ns.y), refined_rcp(ns.z), refined_rcp(ns.w));
     __syncthreads();
     if (a + 1 < n_s && gvalid) ns = __ldg(reinterpret_cast<const float4*>(s_grid + (int64_t)(a + 1) * K + gcol));
     float2 sv[8], x[8];
@@ -484,7 +487,8 @@ fakequant_delta_v4(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
       const float2 sc2 = make_float2(fg.scale, fg.scale);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float2 rs = make_float2(refined_rcp(sv[i].x), refined_rcp(sv[i].y));
+        const float4 rr = *reinterpret_cast<const float4*>(&sm_r[buf][ld_off[i >> 1]]);
+        const float2 rs = (i & 1) ? make_float2(rr.z, rr.w) : make_float2(rr.x, rr.y);
         const float2 q0 = __fmul2_rn(x[i], r2);
         const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x[i]), r2, q0);            // x / scale, exact
         float2 v = __fadd2_rn(q, zp2);
