@@ -117,7 +117,7 @@ class SearchPipeline:
         self.grid_cache = {}
         self.pending = []
         self.i = 0
-        self._err_block, self._err_used = None, 0
+        self._err_blocks, self._err_used = [], 0
         self._events, self._ev_i = [], 0
         self._last_cur_sync = None
 
@@ -138,15 +138,17 @@ class SearchPipeline:
             self.grid_cache[key] = (s_grid, xb, rws, x)
         return self.grid_cache[key]
 
-    def _err_row(self) -> torch.Tensor:
-        """rows of one pre-zeroed fp64 block (no per-tensor allocation / memset launch)"""
-        if self._err_block is None or self._err_used == self._err_block.shape[0]:
+    def _err_row(self):
+        """rows of pre-zeroed fp64 blocks (no per-tensor allocation / memset launch); returns
+        (row tensor, block index, row index)"""
+        if not self._err_blocks or self._err_used == self._err_blocks[-1].shape[0]:
             with torch.cuda.stream(self.s_prep):
-                self._err_block = torch.zeros((256, self.n_grid), dtype=torch.float64, device=self.dev)
+                self._err_blocks.append(torch.zeros((256, self.n_grid), dtype=torch.float64, device=self.dev))
             self._err_used = 0
-        row = self._err_block[self._err_used]
+        row = self._err_blocks[-1][self._err_used]
+        where = (len(self._err_blocks) - 1, self._err_used)
         self._err_used += 1
-        return row
+        return row, where
 
     def submit(self, name: str, w: torch.Tensor, x: torch.Tensor) -> None:
         _check(w, x, self.g)
@@ -165,7 +167,7 @@ class SearchPipeline:
             with torch.cuda.stream(self.s_prep):
                 self.bufs[b] = torch.empty(need, dtype=torch.bfloat16, device=self.dev)
         s_grid, xb, rws, _ = self._grid(x)
-        err = self._err_row()
+        err, where = self._err_row()
         sp, sg = self.s_prep.cuda_stream, self.s_gemm.cuda_stream
         N.check(L.awqk_fakequant_delta(w.data_ptr(), N.dtype_code(w.dtype), C, K, self.g, self.bits, int(self.sym),
                                        s_grid.data_ptr(), self.n_grid, self.bufs[b].data_ptr(), rws.data_ptr(), sp),
@@ -178,7 +180,7 @@ class SearchPipeline:
         done = self._event()
         done.record(self.s_gemm)
         self.buf_free[b] = done
-        self.pending.append((name, err, s_grid, float(T * C), w, x))
+        self.pending.append((name, where, s_grid, float(T * C), w, x))
 
     def _event(self):
         if self._ev_i == len(self._events):
@@ -189,18 +191,33 @@ class SearchPipeline:
 
     def finish(self):
         """joins both streams into the current one; returns [(name, err_mean fp64[n_grid] (device),
-        best_idx (device int64 0-d), s_best (device fp32 [K]))] without a host sync"""
+        best_idx (device int64 0-d), s_best (device fp32 [K]))] without a host sync.  The argmin and the
+        gather of the winning scale vectors are batched: one launch per error block / activation tensor."""
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_stream(self.s_prep)
         cur.wait_stream(self.s_gemm)
-        out = []
-        for name, err, s_grid, denom, w, x in self.pending:
-            mean = err / denom
-            best = torch.argmin(mean)
-            out.append((name, mean, best, s_grid.index_select(0, best.reshape(1))[0]))
+        if not self.pending:
+            return []
+        n = len(self.pending)
+        denom = torch.tensor([p[3] for p in self.pending], dtype=torch.float64, device=self.dev)
+        rows = []
+        for bi, blk in enumerate(self._err_blocks):
+            cnt = sum(1 for p in self.pending if p[1][0] == bi)
+            rows.append(blk[:cnt])
+        means = torch.cat(rows) / denom[:, None]                  # pending order == allocation order
+        best = torch.argmin(means, dim=1)                         # first minimum -> smallest alpha on ties
+        s_best = [None] * n
+        by_grid = {}
+        for i, p in enumerate(self.pending):
+            by_grid.setdefault(id(p[2]), (p[2], []))[1].append(i)
+        for s_grid, idxs in by_grid.values():
+            sel = s_grid.index_select(0, best)                    # [n, K] rows for every tensor: no index upload
+            for i in idxs:
+                s_best[i] = sel[i]
+        out = [(p[0], means[i], best[i], s_best[i]) for i, p in enumerate(self.pending)]
         self.pending = []
         self._ev_i = 0                       # events are reusable once both streams were joined
-        self._err_block = None
+        self._err_blocks, self._err_used = [], 0
         return out
 
 

@@ -173,3 +173,28 @@ print("ok")
         r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, AWQK_GEMM_2CTA=flag),
                            capture_output=True, text=True, timeout=240)
         assert r.returncode == 0 and "ok" in r.stdout, (flag, r.stderr[-1500:])
+
+
+def test_search_pipeline_matches_per_tensor_search(native_lib, cuda_device):
+    """SearchPipeline (two streams, batched argmin) == search_device per tensor"""
+    from awq_quantizer.quantization.search import SearchPipeline, search_device
+    dev = cuda_device
+    X1 = datagen.activations(160, 256, "bf16", 1).to(dev)
+    X2 = datagen.activations(96, 512, "bf16", 2).to(dev)
+    ws = {"a": (datagen.weights((64, 256), "bf16", 3).to(dev), X1), "b": (datagen.weights((128, 256), "bf16", 4).to(dev), X1),
+          "c": (datagen.weights((32, 512), "bf16", 5).to(dev), X2), "d": (datagen.weights((256, 256), "fp16", 6).to(dev), X1)}
+    pipe = SearchPipeline(dev, bits=4, group_size=128, symmetric=False, n_grid=8)
+    for rep in range(2):                      # second round reuses events / buffers
+        for n, (w, x) in ws.items():
+            pipe.submit(n, w, x)
+        res = {name: (mean, best, sb) for name, mean, best, sb in pipe.finish()}
+        torch.cuda.synchronize()
+        assert list(res) == list(ws)
+        for n, (w, x) in ws.items():
+            r = search_device(w, x, bits=4, group_size=128, symmetric=False, n_grid=8)
+            want = (r["err_sum"] / float(x.shape[0] * w.shape[0])).cpu()
+            got = res[n][0].cpu()
+            assert torch.allclose(got, want, rtol=1e-9, atol=0), n       # same kernels; fp64 atomics order only
+            b = int(torch.argmin(want))
+            assert int(res[n][1]) == b
+            assert torch.equal(res[n][2].cpu(), r["s_grid"][b].cpu())
