@@ -218,6 +218,8 @@ def main(argv=None) -> int:
         os.makedirs(args.output_dir, exist_ok=True)
         rank, world = parallel.init_distributed()
         local = parallel.rank_info()[2]
+        if world > 1:
+            parallel.bind_to_gpu_numa(local)
 
         if world > 1:
             devices = [f"cuda:{local}"]

@@ -187,6 +187,8 @@ def run_native(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    from awq_quantizer import parallel
+    numa_node = parallel.bind_to_gpu_numa(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -357,7 +359,8 @@ def run_native(args):
                                f"{'symmetric' if sym else 'asymmetric'}, arith={args.arith}",
                    "tensors_per_rank": len(shapes), "params_per_rank": payload_elems,
                    "l2": "inputs larger than L2 (arena %.0f MB per pass)" % (n_arena * 2 / 1e6),
-                   "parallelism": f"tensor-sharded x{world}, no data-path collective", "launch": graph_mode},
+                   "parallelism": f"tensor-sharded x{world}, no data-path collective", "launch": graph_mode,
+                   "numa_node_rank0": numa_node},
         "s_per_model": ms_step * 1e-3, "roofline": roofline,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "s_per_model": dt / e2e_steps, "api": "AWQQuantizer.quantize_model(HostArena, pack=True)",
