@@ -450,7 +450,7 @@ static int launch_generic(const InT* w, int64_t C, int64_t K, int g, int64_t G, 
 
 // awqk_group_quant_tma.cu
 int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, bool sym, int arith,
-                           uint32_t* q_packed, void* scales, int32_t* zp, uint32_t* zp_packed,
+                           uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                            cudaStream_t st);
 
 static bool tma_path_enabled() {
@@ -505,11 +505,10 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
     }
     const int64_t n = C * K;
     int rc;
-    if (bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) && q_unpacked == nullptr &&
-        q_packed != nullptr && col_scale == nullptr && tma_path_enabled() &&
-        (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0) {
-      // K1 v2: TMA-staged, packed-math kernel (the headline int4 pack path)
-      rc = launch_group_quant_tma(w, dtype, n, group_size, sym, arith, q_packed, scales_f16, zp,
+    if (bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) && (q_packed != nullptr || q_unpacked != nullptr) &&
+        col_scale == nullptr && tma_path_enabled() && (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0) {
+      // K1 v2: TMA-staged, packed-math kernel (int4 pack path and the reference's int32 code layout)
+      rc = launch_group_quant_tma(w, dtype, n, group_size, sym, arith, q_packed, q_unpacked, scales_f16, zp,
                                   out.zp_packed, st);
     } else
     // fp32 arithmetic for any input when arith == FP32; otherwise the input's own dtype

@@ -163,13 +163,20 @@ struct PairQuant<AR_F16, QMIN> {
 };
 
 struct V2Out {
-  uint32_t* q_packed;
+  uint32_t* q_packed;   // nullable when q_unpacked is given
+  int32_t* q_unpacked;  // nullable; only the UNPACKED instantiations look at it
   __half* scales;
   int32_t* zp;          // nullable
   uint32_t* zp_packed;  // nullable (flat layout only)
 };
 
-template <typename InT, int A, int G, bool SYM>
+// UNPACKED: additionally emits the reference's int32 code tensor (awq.py:329, 4 B per element).  The 32
+// codes of a thread (128 B) would cost 32 L1 wavefronts per store instruction if written directly, so
+// each warp transposes its 1024 codes through a private 4 KiB shared staging area (XOR-swizzled, both
+// directions conflict-free) and stores 512 contiguous bytes per instruction.
+constexpr int kV2UnpStageBytes = kV2ConsumerWarps * kV2WarpTile * 4;   // 32 KiB per CTA
+
+template <typename InT, int A, int G, bool SYM, bool UNPACKED>
 __global__ void __launch_bounds__(kV2Threads, 3)
 group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out) {
   constexpr int LPG = G / 32;            // lanes per group (4, 2, 1)
@@ -178,7 +185,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + 15);
 
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kV2Stages * kV2StageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kV2Stages * kV2StageBytes + (UNPACKED ? kV2UnpStageBytes : 0));
   uint32_t full0 = smem_u32(bars);
   uint32_t empty0 = smem_u32(bars + kV2Stages);
   asm volatile("" : "+r"(full0), "+r"(empty0));   // keep the shared-window addresses in registers
@@ -249,6 +256,25 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   const uint32_t zq_shift = 4u * ((uint32_t)(lane / LPG) & 7u);
   const uint32_t zq_mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
 
+  // UNPACKED: warp-private staging of 256 x 16 B chunks.  Thread l owns logical chunks 8l..8l+7 (4 codes
+  // each); chunk j is stored at 8l + (j ^ (l & 7)); store instruction t reads logical chunk 32t + l.
+  uint32_t stg_w[8], stg_r[8];
+  uint8_t* qu_base = nullptr;
+  const bool has_qp = out.q_packed != nullptr;
+  if (UNPACKED) {
+    const uint32_t stg0 = smem_u32(smem) + kV2Stages * kV2StageBytes + (uint32_t)warp * (kV2WarpTile * 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      stg_w[j] = stg0 + (uint32_t)((8 * lane + (j ^ (lane & 7))) << 4);
+      const int o = 4 * j + (lane >> 3);                       // owner lane of logical chunk 32j + lane
+      stg_r[j] = stg0 + (uint32_t)((8 * o + ((lane & 7) ^ (o & 7))) << 4);
+    }
+    // this lane's first coalesced chunk of the warp tile: element 4 * lane
+    qu_base = reinterpret_cast<uint8_t*>(out.q_unpacked + tile0 * kV2CtaTile + (int64_t)warp * kV2WarpTile + 4 * lane);
+  }
+  const uint32_t qu_step = (uint32_t)e_stride * 4u;              // bytes per iteration (grid <= 3 * SMs)
+  const int64_t warp_e_first = tile0 * kV2CtaTile + (int64_t)warp * kV2WarpTile;
+
   PairQuant<A, QMIN> pq;
   pq.prepare();
   uint32_t stage = 0, ph = 0;
@@ -289,6 +315,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     const FastGroup fg = group_params_fast<A, 4>(mn, mx, SYM, FQMIN, FQMAX);
     float sc = fg.scale, zp = fg.zp;
     uint32_t words[4];
+    uint32_t nanmask = 0;            // UNPACKED: bit e <=> code of logical element e is NaN (INT32_MIN)
     // tighter than group_params_fast: the packed 16-bit clamp needs round(x/s + zp) inside the
     // range where the magic-constant add is linear and the s16 rebase cannot wrap
     //   fp32 : |x|/s < 2^14 (low half of the fp32 magic sum is an s16)
@@ -332,6 +359,11 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
           const uint32_t u1 = (c1 == INT32_MIN) ? 0u : (uint32_t)(c1 - QMIN);
           acc |= (u0 & 15u) << (8 * p);
           acc |= (u1 & 15u) << (8 * p + 4);
+          if (UNPACKED) {            // slot wi holds logical 16-byte chunk (wi + rot) & 3
+            const int e = 8 * ((wi + rot) & 3) + 2 * p;
+            nanmask |= (c0 == INT32_MIN ? 1u : 0u) << e;
+            nanmask |= (c1 == INT32_MIN ? 1u : 0u) << (e + 1);
+          }
         }
         words[wi] = acc;
       }
@@ -343,7 +375,38 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     uint32_t o0 = words[0], o1 = words[1], o2 = words[2], o3 = words[3];
     if (rot & 1) { const uint32_t t = o3; o3 = o2; o2 = o1; o1 = o0; o0 = t; }
     if (rot & 2) { uint32_t t = o0; o0 = o2; o2 = t; t = o1; o1 = o3; o3 = t; }
-    if (valid) st_stream16(q_base + (uint64_t)it * q_step, make_uint4(o0, o1, o2, o3));
+    if (valid && (!UNPACKED || has_qp)) st_stream16(q_base + (uint64_t)it * q_step, make_uint4(o0, o1, o2, o3));
+    if (UNPACKED) {
+      const uint32_t ow[4] = {o0, o1, o2, o3};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // 8 nibbles -> 8 int32 codes: even nibbles / odd nibbles to bytes, then one PRMT per code
+        const uint32_t ev = ow[k] & 0x0F0F0F0Fu, od = (ow[k] >> 4) & 0x0F0F0F0Fu;
+        int c[8];
+        c[0] = (int)__byte_perm(ev, 0u, 0x4440) + QMIN; c[1] = (int)__byte_perm(od, 0u, 0x4440) + QMIN;
+        c[2] = (int)__byte_perm(ev, 0u, 0x4441) + QMIN; c[3] = (int)__byte_perm(od, 0u, 0x4441) + QMIN;
+        c[4] = (int)__byte_perm(ev, 0u, 0x4442) + QMIN; c[5] = (int)__byte_perm(od, 0u, 0x4442) + QMIN;
+        c[6] = (int)__byte_perm(ev, 0u, 0x4443) + QMIN; c[7] = (int)__byte_perm(od, 0u, 0x4443) + QMIN;
+        if (nanmask != 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if ((nanmask >> (8 * k + i)) & 1u) c[i] = INT32_MIN;
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stg_w[2 * k]), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stg_w[2 * k + 1]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]) : "memory");
+      }
+      __syncwarp();
+      // whole 16-byte chunks are valid or not: the tensor ends on a group (>= 32 element) boundary
+      const int64_t warp_e0 = warp_e_first + (int64_t)it * e_stride;
+      uint8_t* dst = qu_base + (uint64_t)it * qu_step;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stg_r[t]));
+        if (warp_e0 + 128 * t + 4 * lane < n_elems) st_stream16(dst + 512 * t, v);
+      }
+      __syncwarp();                                    // staging is reused by the next tile
+    }
     if (valid && leader) {
       *reinterpret_cast<__half*>(s_base + (uint64_t)it * s_step) = __float2half_rn(sc);
       if (has_zp) *reinterpret_cast<int32_t*>(z_base + (uint64_t)it * z_step) = zi;
@@ -356,25 +419,25 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   }
 }
 
-template <typename InT, int A, int G>
+template <typename InT, int A, int G, bool UNPACKED>
 static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, cudaStream_t st) {
   const int64_t n_tiles = ceil_div(n, kV2CtaTile);
   int dev = 0, sms = 0;
   AWQK_CUDA(cudaGetDevice(&dev));
   AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t want = (int64_t)sms * 3;
+  const int64_t want = (int64_t)sms * (UNPACKED ? 2 : 3);          // resident CTAs per SM (shared-memory bound)
   const unsigned grid = (unsigned)(n_tiles < want ? n_tiles : want);
-  const size_t smem = (size_t)kV2Stages * kV2StageBytes + 2 * kV2Stages * sizeof(uint64_t);
+  const size_t smem = (size_t)kV2Stages * kV2StageBytes + (UNPACKED ? kV2UnpStageBytes : 0) + 2 * kV2Stages * sizeof(uint64_t);
   // the dynamic-smem opt-in is per (kernel instantiation, device): set once, then immutable
   static std::atomic<uint64_t> configured[2] = {{0}, {0}};
   const uint64_t bit = 1ull << (dev & 63);
   const bool need = !(configured[sym ? 1 : 0].load(std::memory_order_acquire) & bit);
   if (sym) {
-    auto k = group_quant_tma<InT, A, G, true>;
+    auto k = group_quant_tma<InT, A, G, true, UNPACKED>;
     if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
   } else {
-    auto k = group_quant_tma<InT, A, G, false>;
+    auto k = group_quant_tma<InT, A, G, false, UNPACKED>;
     if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
   }
@@ -385,19 +448,26 @@ static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, cudaStrea
 
 template <typename InT, int A>
 static int launch_v2_g(const InT* w, int64_t n, int g, bool sym, V2Out out, cudaStream_t st) {
+  if (out.q_unpacked != nullptr) {
+    switch (g) {
+      case 32: return launch_v2_sym<InT, A, 32, true>(w, n, sym, out, st);
+      case 64: return launch_v2_sym<InT, A, 64, true>(w, n, sym, out, st);
+      default: return launch_v2_sym<InT, A, 128, true>(w, n, sym, out, st);
+    }
+  }
   switch (g) {
-    case 32: return launch_v2_sym<InT, A, 32>(w, n, sym, out, st);
-    case 64: return launch_v2_sym<InT, A, 64>(w, n, sym, out, st);
-    default: return launch_v2_sym<InT, A, 128>(w, n, sym, out, st);
+    case 32: return launch_v2_sym<InT, A, 32, false>(w, n, sym, out, st);
+    case 64: return launch_v2_sym<InT, A, 64, false>(w, n, sym, out, st);
+    default: return launch_v2_sym<InT, A, 128, false>(w, n, sym, out, st);
   }
 }
 
 // Entry used by awqk_group_quant: int4, bf16/fp16 input, packed output only, flat layout
 // (K % g == 0, g in {32,64,128}, 16-byte aligned base).  zp_packed must be null unless G % 8 == 0.
 int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, bool sym, int arith,
-                           uint32_t* q_packed, void* scales, int32_t* zp, uint32_t* zp_packed,
+                           uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                            cudaStream_t st) {
-  V2Out out{q_packed, reinterpret_cast<__half*>(scales), zp, zp_packed};
+  V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed};
   if (dtype == AWQK_BF16) {
     auto p = reinterpret_cast<const __nv_bfloat16*>(w);
     return arith == AWQK_ARITH_FP32 ? launch_v2_g<__nv_bfloat16, AR_F32>(p, n_elems, g, sym, out, st)

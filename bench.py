@@ -288,6 +288,12 @@ def run_native(args):
             ms = float(t.item())
         return ms / steps
 
+    # clock ramp: a freshly leased GPU idles at ~120 MHz; run the step for ~0.2 s before the W warm-up steps
+    t_ramp = time.perf_counter()
+    while time.perf_counter() - t_ramp < 0.2:
+        for _ in range(50):
+            step_device()
+        torch.cuda.synchronize(dev)
     clocks = ClockSampler(local)
     clocks.start()
     ms_step = timed(step_device, args.steps, max(3, args.warmup))
