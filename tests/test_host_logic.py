@@ -83,3 +83,23 @@ def test_quantize_model_swallows_per_tensor_errors():
 def test_layout_rules(shape, pc, expect):
     q = mk(per_channel=pc)
     assert q._layout(torch.zeros(shape)) == expect
+
+
+def test_model_shape_inventories_match_survey():
+    """parameter counts of the BASELINE.json model shapes"""
+    from awq_quantizer import model_shapes as M
+    assert M.total_params(M.workload("opt-125m")) == 125_237_760
+    assert abs(M.total_params(M.workload("opt-350m")) / 1e9 - 0.331) < 0.001
+    assert abs(M.total_params(M.workload("llama3-8b")) / 1e9 - 8.030) < 0.001
+    assert abs(M.total_params(M.workload("llama3-70b")) / 1e9 - 70.55) < 0.01
+    assert [s for _, s, _ in M.workload("test_quantization")] == [(768, 3072), (768, 3, 768), (10, 10)]
+    assert M.workload("micro-8192x28672")[0][1] == (8192, 28672)
+    lin = [s for _, s, ck in M.workload("llama3-8b") if ck is not None]
+    assert len(lin) == 32 * 7 and sum(a * b for a, b in lin) == 6_979_321_856     # 6.979 B linear params
+
+
+def test_numa_binding_is_best_effort():
+    from awq_quantizer import parallel
+    assert parallel.bind_to_gpu_numa(0) in (None, 0, 1, 2, 3, 4, 5, 6, 7)        # never raises (no GPU here -> None)
+    assert parallel.rank_info() == (0, 1, 0)
+    assert parallel.gather_metadata({"rank": 0}) == [{"rank": 0}]
