@@ -3,7 +3,8 @@ on the B200 path:
 
 * every flag of main.py:32-157 is accepted unchanged; additive flags: ``--pack`` (int32-packed
   qweight/qzeros next to or instead of the unpacked codes), ``--arith {native,fp32}``, ``--config``
-  (the YAML file the reference documents but never wired, main.py:16 / USAGE.md:13-22);
+  (the YAML file the reference documents but never wired, main.py:16 / USAGE.md:13-22),
+  ``--calibration_file`` / ``--n_grid`` (activation-aware alpha search for the weights it names);
 * tensor selection = main.py:243-253 (non-float / empty / numel < 128 are skipped, largest first);
 * ``--multi_gpu`` no longer repeats the whole model on every device (main.py:596-606): tensors are
   partitioned largest-first onto the least-loaded device -- the reference's own, never-called,
@@ -64,6 +65,10 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--arith", type=str, default="native", choices=["native", "fp32"],
                    help="arithmetic contract: native = the reference's own (input dtype), fp32 = reference on w.float()")
     p.add_argument("--config", type=str, help="YAML config (reference schema); CLI flags win over it")
+    p.add_argument("--calibration_file", type=str,
+                   help="safetensors file {weight name: activations [tokens, in_features]}: run the "
+                        "activation-aware alpha search (scale_method) for those weights")
+    p.add_argument("--n_grid", type=int, default=20, help="points of the alpha grid for --calibration_file")
     return p.parse_args(argv)
 
 
@@ -254,13 +259,23 @@ def main(argv=None) -> int:
         else:                                            # one process, 1..N devices
             shards = partition_tensors(quantizable, len(devices))
 
+        calib = {}
+        if args.calibration_file:
+            from safetensors.torch import load_file
+            calib = load_file(args.calibration_file)
+            logger.info(f"Loaded calibration activations for {len(calib)} tensors")
+
         def run_device(device: str, shard: Dict[str, torch.Tensor]) -> Dict[str, dict]:
             qz = AWQQuantizer(bits=args.bits, group_size=args.group_size, symmetric=args.symmetric,
                               zero_point=args.zero_point, percentile=args.percentile, scale_method=args.scale_method,
                               per_channel=args.per_channel, device=device, logger_name=f"awq_quantizer_{device}",
                               logger_level=args.log_level, logger_to_file=args.log_file is not None,
-                              logger_file_path=args.log_file, arith=args.arith)
+                              logger_file_path=args.log_file, arith=args.arith, n_grid=args.n_grid)
             done: Dict[str, dict] = {}
+            searched = {n: t for n, t in shard.items() if n in calib and t.dim() == 2}
+            if searched:
+                done.update(qz.quantize_model(searched, activations={n: calib[n] for n in searched}, pack=args.pack))
+                shard = {n: t for n, t in shard.items() if n not in done}
             batches = prepare_tensors_for_quantization(shard, device, args.max_memory, args.batch_size, logger)
             with ThreadPoolExecutor(max_workers=max(1, args.num_workers)) as ex:
                 futs = [ex.submit(quantize_tensor_batch, list(b.items()), qz, device, logger, args.pack) for b in batches]

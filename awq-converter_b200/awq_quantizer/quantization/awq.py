@@ -194,7 +194,8 @@ class AWQQuantizer:
         return out
 
     # ------------------------------------------------------------------ awq.py:435-457
-    def quantize_model(self, tensors, *, pack: bool = False, chunk_bytes: int = 32 << 20, pipeline: bool = True):
+    def quantize_model(self, tensors, *, pack: bool = False, chunk_bytes: int = 32 << 20, pipeline: bool = True,
+                       activations: Optional[Dict[str, torch.Tensor]] = None):
         """dict-in / dict-out; a tensor that raises is logged and skipped (awq.py:453-455).
 
         ``pack=False`` (default): the reference's result layout per tensor (``tensor_q`` int32, ``scales``
@@ -203,7 +204,23 @@ class AWQQuantizer:
         whole packed-zero words) goes through ONE flat arena per dtype and the chunked H2D -> K1 -> D2H
         pipeline (quantization/arena.py) instead of a per-tensor upload / kernel / download sequence;
         the results are then views of pinned host arenas.  ``pipeline=False`` forces the per-tensor loop.
-        ``tensors`` may already be a ``HostArena`` (zero-copy)."""
+        ``tensors`` may already be a ``HostArena`` (zero-copy).
+
+        ``activations`` (name -> calibration activations [tokens, in_features]) turns on the activation-aware
+        alpha search for those tensors (quantization/search.py); all other tensors take the paths above."""
+        if activations:
+            from .search import quantize_model_with_search
+            dev = self._cuda_device()
+            self._check_zero_point_mode()
+            searched = {}
+            try:
+                searched = quantize_model_with_search(self, {n: t for n, t in tensors.items() if n in activations},
+                                                      activations, dev, pack=pack)
+            except Exception as e:
+                self.logger.error(f"Activation-aware search failed: {e}")
+            rest = {n: t for n, t in tensors.items() if n not in searched}
+            other = self.quantize_model(rest, pack=pack, chunk_bytes=chunk_bytes, pipeline=pipeline) if rest else {}
+            return {n: (searched[n] if n in searched else other[n]) for n in tensors if n in searched or n in other}
         if not pack:
             from .arena import HostArena, pipe_eligible, quantize_arena
             quantized, rest = {}, tensors

@@ -221,6 +221,56 @@ class SearchPipeline:
         return out
 
 
+def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations: Dict[str, torch.Tensor],
+                               dev: torch.device, *, pack: bool = False,
+                               wave_bytes: int = 8 << 30) -> Dict[str, Dict[str, torch.Tensor]]:
+    """Model-level AWQ: every 2-D tensor that has calibration activations goes through the overlapped
+    search pipeline (SearchPipeline) and the final K1 pass on W * s_best; the host sees one
+    synchronisation per wave of ``wave_bytes`` of weights.  Results carry the reference's keys plus
+    ``awq_scale`` / ``alpha`` / ``best_idx`` / ``search_err`` (+ ``qweight`` / ``qzeros`` with pack)."""
+    names = [n for n, t in tensors.items() if n in activations]
+    for n in names:
+        _check(tensors[n], activations[n], qz.group_size)
+    out: Dict[str, Dict[str, torch.Tensor]] = {}
+    x_dev: Dict[int, torch.Tensor] = {}
+    pipe = SearchPipeline(dev, bits=qz.bits, group_size=qz.group_size, symmetric=qz.symmetric, n_grid=qz.n_grid)
+    i = 0
+    while i < len(names):
+        wave, nbytes = [], 0
+        while i < len(names) and (not wave or nbytes + tensors[names[i]].numel() * 2 <= wave_bytes):
+            wave.append(names[i])
+            nbytes += tensors[names[i]].numel() * tensors[names[i]].element_size()
+            i += 1
+        w_dev = {}
+        for n in wave:
+            x = activations[n]
+            if id(x) not in x_dev:
+                x_dev[id(x)] = x.to(dev, non_blocking=True).contiguous()
+            w_dev[n] = tensors[n].to(dev, non_blocking=True).contiguous()
+            pipe.submit(n, w_dev[n], x_dev[id(x)])
+        res = pipe.finish()
+        finals = {}
+        for name, mean, best, s_best in res:
+            finals[name] = (qz._quantize_device(w_dev[name], pack=pack, col_scale=s_best.contiguous(), arith="fp32"),
+                            mean, best, s_best)
+        for name, (o, mean, best, s_best) in finals.items():
+            o = dict(o)
+            o.update({"search_err": mean, "best_idx": best.to(torch.int32), "awq_scale": s_best})
+            host = qz._to_host(o, dev)
+            b = int(host["best_idx"])
+            r = {"tensor_q": host["tensor_q"], "scales": host["scales"], "zero_points": host["zero_points"],
+                 "bits": torch.tensor(qz.bits, dtype=torch.int32),
+                 "group_size": torch.tensor(qz.group_size, dtype=torch.int32),
+                 "symmetric": torch.tensor(qz.symmetric, dtype=torch.bool),
+                 "awq_scale": host["awq_scale"], "alpha": torch.tensor(b / qz.n_grid, dtype=torch.float32),
+                 "best_idx": host["best_idx"], "search_err": host["search_err"]}
+            if pack:
+                r["qweight"], r["qzeros"] = host["qweight"], host["qzeros"]
+            out[name] = r
+        del w_dev, finals
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def smoke_check() -> None:
     """tiny end-to-end search on cuda:0 against the oracle (called by __graft_entry__.smoke)"""

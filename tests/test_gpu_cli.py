@@ -68,3 +68,24 @@ def test_cli_multi_gpu_flag_partitions_instead_of_repeating(native_lib, cuda_dev
     assert rc == 0
     md = json.load(open(os.path.join(out, "metadata.json")))
     assert md["num_tensors"] == 4
+
+
+def test_cli_calibration_file_runs_search(native_lib, cuda_device, tmp_path):
+    from safetensors.torch import save_file
+    from awq_quantizer import main as cli
+    from awq_quantizer.quantization import AWQQuantizer
+    model, tensors = make_model(tmp_path)
+    X = datagen.activations(96, 256, "bf16", 9)
+    calib = str(tmp_path / "calib.safetensors")
+    save_file({"layers.0.fc1.weight": X}, calib)
+    out = str(tmp_path / "out_awq")
+    rc = cli.main(["--model_id", model, "--output_dir", out, "--device", "cuda:0", "--calibration_file", calib,
+                   "--n_grid", "8", "--pack", "--log_level", "ERROR", "--chunk_size", "100"])
+    assert rc == 0
+    got = torch.load(os.path.join(out, "model_chunk_0000.pt"))
+    qz = AWQQuantizer(bits=4, group_size=128, symmetric=False, per_channel=False, device="cuda:0", logger_level="ERROR", n_grid=8)
+    want = qz.quantize(tensors["layers.0.fc1.weight"], activations=X, pack=True)
+    r = got["layers.0.fc1.weight"]
+    assert int(r["best_idx"]) == int(want["best_idx"]) and torch.equal(r["qweight"], want["qweight"])
+    assert torch.equal(r["awq_scale"], want["awq_scale"])
+    assert "awq_scale" not in got["layers.0.fc2.weight"]

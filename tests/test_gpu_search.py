@@ -198,3 +198,25 @@ def test_search_pipeline_matches_per_tensor_search(native_lib, cuda_device):
             b = int(torch.argmin(want))
             assert int(res[n][1]) == b
             assert torch.equal(res[n][2].cpu(), r["s_grid"][b].cpu())
+
+
+def test_quantize_model_with_activations(native_lib, cuda_device):
+    """model-level AWQ through the public API: searched linears + plain tensors in one call"""
+    from awq_quantizer.quantization import AWQQuantizer
+    X1 = datagen.activations(128, 256, "bf16", 1)
+    X2 = datagen.activations(96, 512, "bf16", 2)
+    tensors = {"q_proj": datagen.weights((128, 256), "bf16", 3), "k_proj": datagen.weights((64, 256), "bf16", 4),
+               "norm": datagen.weights((256,), "bf16", 5), "down": datagen.weights((64, 512), "bf16", 6)}
+    acts = {"q_proj": X1, "k_proj": X1, "down": X2}
+    qz = AWQQuantizer(bits=4, group_size=128, symmetric=False, device="cuda:0", logger_level="ERROR", n_grid=10)
+    out = qz.quantize_model(tensors, activations=acts, pack=True, )
+    assert list(out) == list(tensors)
+    for n in acts:
+        single = qz.quantize(tensors[n], activations=acts[n], pack=True)
+        assert int(out[n]["best_idx"]) == int(single["best_idx"])
+        assert torch.equal(out[n]["awq_scale"], single["awq_scale"])
+        assert_quant_equal(out[n], single, n, keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
+        assert torch.allclose(out[n]["search_err"], single["search_err"], rtol=1e-9)
+    want = O.pack_result(O.group_quant_vec(tensors["norm"], 4, 128, False, True))
+    assert_same(out["norm"]["qweight"], want["qweight"], "norm")
+    assert "awq_scale" not in out["norm"]
