@@ -453,6 +453,11 @@ int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, boo
                            uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                            cudaStream_t st);
 
+bool group_quant_tma_cs_eligible(int64_t C, int64_t K);
+int launch_group_quant_tma_cs(const void* w, int dtype, int64_t C, int64_t K, int g, bool sym, const float* col_scale,
+                              uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
+                              cudaStream_t st);
+
 static bool tma_path_enabled() {
   // AWQK_FORCE_V1=1 keeps the register-path kernel for A/B measurements (read once, read-only)
   static const bool enabled = []() {
@@ -510,6 +515,12 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
       // K1 v2: TMA-staged, packed-math kernel (int4 pack path and the reference's int32 code layout)
       rc = launch_group_quant_tma(w, dtype, n, group_size, sym, arith, q_packed, q_unpacked, scales_f16, zp,
                                   out.zp_packed, st);
+    } else if (bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) && (q_packed != nullptr || q_unpacked != nullptr) &&
+               col_scale != nullptr && tma_path_enabled() && (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0 &&
+               group_quant_tma_cs_eligible(C, K)) {
+      // K1 v2 CS: the same kernel walking column slabs, per-input-channel scales in registers (final AWQ pass)
+      rc = launch_group_quant_tma_cs(w, dtype, C, K, group_size, sym, col_scale, q_packed, q_unpacked, scales_f16, zp,
+                                     out.zp_packed, st);
     } else
     // fp32 arithmetic for any input when arith == FP32; otherwise the input's own dtype
     if (dtype == AWQK_BF16) {

@@ -176,9 +176,32 @@ struct V2Out {
 // directions conflict-free) and stores 512 contiguous bytes per instruction.
 constexpr int kV2UnpStageBytes = kV2ConsumerWarps * kV2WarpTile * 4;   // 32 KiB per CTA
 
-template <typename InT, int A, int G, bool SYM, bool UNPACKED>
-__global__ void __launch_bounds__(kV2Threads, 3)
-group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out) {
+// CS ("column scaled", the final AWQ pass: quantize fp32(w) * s[k], awqk.h col_scale): the tensor is cut
+// into column slabs of 1024 (one warp tile wide); a CTA owns ONE slab and walks down it 8 rows per stage
+// (8 bulk copies of 2 KiB, one per consumer warp), so a thread's 32 columns never change and their
+// scales live in registers for the whole kernel.  Requires K % 1024 == 0: every output offset is then
+// still (thread base) + it * (constant stride) in the flat row-major arrays, exactly as in the flat mode.
+struct V2ColScale {
+  const float* s;     // [K]
+  int64_t K, C;
+  int n_slabs, cps;   // K / 1024, CTAs per slab (grid = n_slabs * cps)
+};
+
+__device__ __forceinline__ float fmin3_nan(float a, float b, float c) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+template <typename InT, int A, int G, bool SYM, bool UNPACKED, bool CS>
+__global__ void __launch_bounds__(kV2Threads, (UNPACKED || CS) ? 2 : 3)
+group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out, V2ColScale csp) {
+  static_assert(!CS || A == AR_F32, "column scaling is defined in fp32 arithmetic");
   constexpr int LPG = G / 32;            // lanes per group (4, 2, 1)
   constexpr int LPW = 8 * LPG;           // lanes per packed zero-point word (32, 16, 8)
   constexpr int QMIN = SYM ? -8 : 0;
@@ -202,11 +225,35 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   }
   __syncthreads();
 
-  const int64_t tile0 = blockIdx.x;
-  const int64_t n_iters = (n_tiles > tile0) ? (n_tiles - tile0 + gridDim.x - 1) / gridDim.x : 0;
+  // flat: CTA b takes tiles b, b + grid, ...   CS: CTA b takes row blocks j, j + cps, ... of slab b % n_slabs
+  const int64_t tile0 = CS ? (int64_t)(blockIdx.x / (unsigned)csp.n_slabs) : (int64_t)blockIdx.x;
+  const int64_t tile_step = CS ? (int64_t)csp.cps : (int64_t)gridDim.x;
+  const int64_t n_iters = (n_tiles > tile0) ? (n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+  const int64_t slab_col = CS ? (int64_t)(blockIdx.x % (unsigned)csp.n_slabs) * kV2WarpTile : 0;
 
   if (warp == kV2ConsumerWarps) {
     // ================= producer: one thread streams CTA tiles into the ring =================
+    if (CS) {
+      if (lane == 0) {
+        const int64_t row_bytes = csp.K * 2;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(w) + (tile0 * kV2ConsumerWarps) * row_bytes + slab_col * 2;
+        const int64_t src_stride = tile_step * kV2ConsumerWarps * row_bytes;
+        int64_t rows_left = csp.C - tile0 * kV2ConsumerWarps;
+        uint32_t stage = 0, ph = 1;
+        for (int64_t it = 0; it < n_iters; ++it) {
+          mbar_wait(empty0 + 8 * stage, ph);
+          const int rows = rows_left < kV2ConsumerWarps ? (int)rows_left : kV2ConsumerWarps;
+          mbar_expect_tx(full0 + 8 * stage, (uint32_t)rows * (kV2WarpTile * 2));
+          const uint32_t dst = smem_u32(smem) + stage * kV2StageBytes;
+          for (int r = 0; r < rows; ++r)
+            bulk_g2s(dst + r * (kV2WarpTile * 2), src + r * row_bytes, kV2WarpTile * 2, full0 + 8 * stage);
+          src += src_stride;
+          rows_left -= tile_step * kV2ConsumerWarps;
+          if (++stage == kV2Stages) { stage = 0; ph ^= 1u; }
+        }
+      }
+      return;
+    }
     if (lane == 0) {
       const uint8_t* src = reinterpret_cast<const uint8_t*>(w) + tile0 * kV2StageBytes;
       const int64_t src_stride = (int64_t)gridDim.x * kV2StageBytes;
@@ -228,9 +275,10 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   // ================================ consumers =================================================
   // per-thread invariants.  Output addresses are (thread base) + it * (byte stride): one IMAD.WIDE
   // per store, no loop-carried 64-bit pointers.
-  const uint32_t thr_elem = (uint32_t)warp * kV2WarpTile + (uint32_t)lane * 32u;     // within the CTA tile
-  const int64_t e_first = tile0 * kV2CtaTile + thr_elem;
-  const int64_t e_stride = (int64_t)gridDim.x * kV2CtaTile;
+  const int64_t warp_e_first = CS ? (tile0 * kV2ConsumerWarps + warp) * csp.K + slab_col
+                                  : tile0 * kV2CtaTile + (int64_t)warp * kV2WarpTile;
+  const int64_t e_first = warp_e_first + (int64_t)lane * 32;
+  const int64_t e_stride = CS ? tile_step * kV2ConsumerWarps * csp.K : tile_step * kV2CtaTile;
   const uint32_t iters = (uint32_t)n_iters;
   // iterations in which this thread's 32 elements exist (whole groups are valid or not)
   const uint32_t valid_iters = (n_elems > e_first) ? (uint32_t)((n_elems - e_first + e_stride - 1) / e_stride) : 0u;
@@ -270,10 +318,22 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
       stg_r[j] = stg0 + (uint32_t)((8 * o + ((lane & 7) ^ (o & 7))) << 4);
     }
     // this lane's first coalesced chunk of the warp tile: element 4 * lane
-    qu_base = reinterpret_cast<uint8_t*>(out.q_unpacked + tile0 * kV2CtaTile + (int64_t)warp * kV2WarpTile + 4 * lane);
+    qu_base = reinterpret_cast<uint8_t*>(out.q_unpacked + warp_e_first + 4 * lane);
   }
-  const uint32_t qu_step = (uint32_t)e_stride * 4u;              // bytes per iteration (grid <= 3 * SMs)
-  const int64_t warp_e_first = tile0 * kV2CtaTile + (int64_t)warp * kV2WarpTile;
+  const uint32_t qu_step = (uint32_t)e_stride * 4u;              // bytes per iteration (host keeps it < 2^32)
+  // CS: this thread's 32 column scales, in the rotated chunk order of the LDS below
+  float2 sreg[CS ? 16 : 1];
+  if (CS) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4* sp = reinterpret_cast<const float4*>(csp.s + slab_col + lane * 32 + 8 * ((c + rot) & 3));
+      const float4 a = __ldg(sp), b = __ldg(sp + 1);
+      sreg[4 * c] = make_float2(a.x, a.y);
+      sreg[4 * c + 1] = make_float2(a.z, a.w);
+      sreg[4 * c + 2] = make_float2(b.x, b.y);
+      sreg[4 * c + 3] = make_float2(b.z, b.w);
+    }
+  }
 
   PairQuant<A, QMIN> pq;
   pq.prepare();
@@ -298,14 +358,32 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     // (threads past the end of the tensor compute on stale shared memory and store nothing)
 
     // ---- group min / max: packed tree over 16 words, then fold halves, then LPG lanes --------
-    uint32_t mn2 = wds[0], mx2 = wds[0];
+    float mn, mx;
+    float2 xv[CS ? 16 : 1];
+    if (CS) {
+      // x = fp32(w) * s[k]; the group statistics are taken on x (3-input FMNMX)
 #pragma unroll
-    for (int i = 1; i < 16; ++i) {
-      mn2 = Packed<InT>::min2(mn2, wds[i]);
-      mx2 = Packed<InT>::max2(mx2, wds[i]);
+      for (int i = 0; i < 16; ++i) xv[i] = __fmul2_rn(Packed<InT>::to_f2(wds[i]), sreg[i]);
+      mn = fmin3_nan(xv[0].x, xv[0].y, xv[1].x);
+      mx = fmax3_nan(xv[0].x, xv[0].y, xv[1].x);
+      mn = v2_fmin_nan(mn, xv[1].y);
+      mx = v2_fmax_nan(mx, xv[1].y);
+#pragma unroll
+      for (int i = 2; i < 16; ++i) {
+        mn = fmin3_nan(mn, xv[i].x, xv[i].y);
+        mx = fmax3_nan(mx, xv[i].x, xv[i].y);
+      }
+    } else {
+      uint32_t mn2 = wds[0], mx2 = wds[0];
+#pragma unroll
+      for (int i = 1; i < 16; ++i) {
+        mn2 = Packed<InT>::min2(mn2, wds[i]);
+        mx2 = Packed<InT>::max2(mx2, wds[i]);
+      }
+      const float2 mnf = Packed<InT>::to_f2(mn2), mxf = Packed<InT>::to_f2(mx2);
+      mn = v2_fmin_nan(mnf.x, mnf.y);
+      mx = v2_fmax_nan(mxf.x, mxf.y);
     }
-    const float2 mnf = Packed<InT>::to_f2(mn2), mxf = Packed<InT>::to_f2(mx2);
-    float mn = v2_fmin_nan(mnf.x, mnf.y), mx = v2_fmax_nan(mxf.x, mxf.y);
 #pragma unroll
     for (int m = 1; m < LPG; m <<= 1) {
       mn = v2_fmin_nan(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, m));
@@ -332,7 +410,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
         uint32_t b3[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const float2 x = Packed<InT>::to_f2(wds[4 * wi + p]);
+          const float2 x = CS ? xv[4 * wi + p] : Packed<InT>::to_f2(wds[4 * wi + p]);
           const float2 q0 = __fmul2_rn(x, r2);
           const float2 e = __ffma2_rn(ns2, q0, x);
           const float2 q = __ffma2_rn(e, r2, q0);                 // correctly rounded x / s
@@ -352,7 +430,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
         uint32_t acc = 0;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const float2 x = Packed<InT>::to_f2(wds[4 * wi + p]);
+          const float2 x = CS ? xv[4 * wi + p] : Packed<InT>::to_f2(wds[4 * wi + p]);
           const int c0 = quant_exact<A>(x.x, sc, zp, FQMIN, FQMAX);
           const int c1 = quant_exact<A>(x.y, sc, zp, FQMIN, FQMAX);
           const uint32_t u0 = (c0 == INT32_MIN) ? 0u : (uint32_t)(c0 - QMIN);
@@ -419,63 +497,94 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   }
 }
 
-template <typename InT, int A, int G, bool UNPACKED>
-static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, cudaStream_t st) {
-  const int64_t n_tiles = ceil_div(n, kV2CtaTile);
+template <typename InT, int A, int G, bool UNPACKED, bool CS>
+static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, V2ColScale csp, cudaStream_t st) {
   int dev = 0, sms = 0;
   AWQK_CUDA(cudaGetDevice(&dev));
   AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t want = (int64_t)sms * (UNPACKED ? 2 : 3);          // resident CTAs per SM (shared-memory bound)
-  const unsigned grid = (unsigned)(n_tiles < want ? n_tiles : want);
+  const int64_t want = (int64_t)sms * ((UNPACKED || CS) ? 2 : 3);   // resident CTAs per SM (smem / register bound)
+  int64_t n_tiles;
+  unsigned grid;
+  if (CS) {
+    n_tiles = ceil_div(csp.C, kV2ConsumerWarps);                     // row blocks of a slab
+    csp.n_slabs = (int)(csp.K / kV2WarpTile);
+    int64_t cps = want / csp.n_slabs;
+    if (cps < 1) cps = 1;
+    if (cps > n_tiles) cps = n_tiles;
+    if (cps > 512) cps = 512;
+    csp.cps = (int)cps;
+    grid = (unsigned)(csp.n_slabs * cps);
+  } else {
+    n_tiles = ceil_div(n, kV2CtaTile);
+    grid = (unsigned)(n_tiles < want ? n_tiles : want);
+  }
   const size_t smem = (size_t)kV2Stages * kV2StageBytes + (UNPACKED ? kV2UnpStageBytes : 0) + 2 * kV2Stages * sizeof(uint64_t);
   // the dynamic-smem opt-in is per (kernel instantiation, device): set once, then immutable
   static std::atomic<uint64_t> configured[2] = {{0}, {0}};
   const uint64_t bit = 1ull << (dev & 63);
   const bool need = !(configured[sym ? 1 : 0].load(std::memory_order_acquire) & bit);
   if (sym) {
-    auto k = group_quant_tma<InT, A, G, true, UNPACKED>;
+    auto k = group_quant_tma<InT, A, G, true, UNPACKED, CS>;
     if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
+    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out, csp);
   } else {
-    auto k = group_quant_tma<InT, A, G, false, UNPACKED>;
+    auto k = group_quant_tma<InT, A, G, false, UNPACKED, CS>;
     if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
+    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out, csp);
   }
   if (need) configured[sym ? 1 : 0].fetch_or(bit, std::memory_order_release);
   AWQK_CUDA(cudaGetLastError());
   return AWQK_OK;
 }
 
-template <typename InT, int A>
-static int launch_v2_g(const InT* w, int64_t n, int g, bool sym, V2Out out, cudaStream_t st) {
+template <typename InT, int A, bool CS>
+static int launch_v2_g(const InT* w, int64_t n, int g, bool sym, V2Out out, V2ColScale csp, cudaStream_t st) {
   if (out.q_unpacked != nullptr) {
     switch (g) {
-      case 32: return launch_v2_sym<InT, A, 32, true>(w, n, sym, out, st);
-      case 64: return launch_v2_sym<InT, A, 64, true>(w, n, sym, out, st);
-      default: return launch_v2_sym<InT, A, 128, true>(w, n, sym, out, st);
+      case 32: return launch_v2_sym<InT, A, 32, true, CS>(w, n, sym, out, csp, st);
+      case 64: return launch_v2_sym<InT, A, 64, true, CS>(w, n, sym, out, csp, st);
+      default: return launch_v2_sym<InT, A, 128, true, CS>(w, n, sym, out, csp, st);
     }
   }
   switch (g) {
-    case 32: return launch_v2_sym<InT, A, 32, false>(w, n, sym, out, st);
-    case 64: return launch_v2_sym<InT, A, 64, false>(w, n, sym, out, st);
-    default: return launch_v2_sym<InT, A, 128, false>(w, n, sym, out, st);
+    case 32: return launch_v2_sym<InT, A, 32, false, CS>(w, n, sym, out, csp, st);
+    case 64: return launch_v2_sym<InT, A, 64, false, CS>(w, n, sym, out, csp, st);
+    default: return launch_v2_sym<InT, A, 128, false, CS>(w, n, sym, out, csp, st);
   }
 }
 
-// Entry used by awqk_group_quant: int4, bf16/fp16 input, packed output only, flat layout
-// (K % g == 0, g in {32,64,128}, 16-byte aligned base).  zp_packed must be null unless G % 8 == 0.
+// Entry used by awqk_group_quant: int4, bf16/fp16 input, flat layout (K % g == 0, g in {32,64,128},
+// 16-byte aligned base).  zp_packed must be null unless G % 8 == 0.
 int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, bool sym, int arith,
                            uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                            cudaStream_t st) {
   V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed};
+  const V2ColScale none{nullptr, 0, 0, 0, 0};
   if (dtype == AWQK_BF16) {
     auto p = reinterpret_cast<const __nv_bfloat16*>(w);
-    return arith == AWQK_ARITH_FP32 ? launch_v2_g<__nv_bfloat16, AR_F32>(p, n_elems, g, sym, out, st)
-                                    : launch_v2_g<__nv_bfloat16, AR_BF16>(p, n_elems, g, sym, out, st);
+    return arith == AWQK_ARITH_FP32 ? launch_v2_g<__nv_bfloat16, AR_F32, false>(p, n_elems, g, sym, out, none, st)
+                                    : launch_v2_g<__nv_bfloat16, AR_BF16, false>(p, n_elems, g, sym, out, none, st);
   }
   auto p = reinterpret_cast<const __half*>(w);
-  return arith == AWQK_ARITH_FP32 ? launch_v2_g<__half, AR_F32>(p, n_elems, g, sym, out, st)
-                                  : launch_v2_g<__half, AR_F16>(p, n_elems, g, sym, out, st);
+  return arith == AWQK_ARITH_FP32 ? launch_v2_g<__half, AR_F32, false>(p, n_elems, g, sym, out, none, st)
+                                  : launch_v2_g<__half, AR_F16, false>(p, n_elems, g, sym, out, none, st);
+}
+
+// Column-scaled entry (col_scale != nullptr, fp32 arithmetic): needs K % 1024 == 0 and the per-iteration
+// output strides below 2^32 bytes; anything else stays on the register path.
+bool group_quant_tma_cs_eligible(int64_t C, int64_t K) {
+  // largest per-iteration stride: cps (<= 512) * 8 rows * K elements * 4 bytes (int32 codes) < 2^32
+  return C > 0 && K % kV2WarpTile == 0 && K <= ((int64_t)1 << 32) / (8 * 4 * 512);
+}
+
+int launch_group_quant_tma_cs(const void* w, int dtype, int64_t C, int64_t K, int g, bool sym, const float* col_scale,
+                              uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
+                              cudaStream_t st) {
+  V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed};
+  const V2ColScale csp{col_scale, K, C, 0, 0};
+  if (dtype == AWQK_BF16)
+    return launch_v2_g<__nv_bfloat16, AR_F32, true>(reinterpret_cast<const __nv_bfloat16*>(w), C * K, g, sym, out, csp, st);
+  return launch_v2_g<__half, AR_F32, true>(reinterpret_cast<const __half*>(w), C * K, g, sym, out, csp, st);
 }
 
 }  // namespace awqk

@@ -1,0 +1,120 @@
+"""GPU (B200): K1 v2 in column-slab mode (csrc/awqk_group_quant_tma.cu, CS = true) -- the final AWQ pass
+`group_quant(fp32(W) * s[k])` -- against the oracle's `quantize_scaled` (the pinned group quantizer
+composed with the per-input-channel scale).  Bit-exact for every output, straight through the C ABI."""
+import pytest
+import torch
+
+from oracle import awq_oracle as O
+from tests import datagen
+from tests.util import assert_same
+
+pytestmark = pytest.mark.gpu
+
+
+def _scales(K, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.exp(0.7 * torch.randn(K, generator=g)).to(torch.float32)
+
+
+def _run(L, N, w, s, g, sym, dev, *, unpacked=True, packed=True, want_zp=True, want_zq=True):
+    C, K = w.shape
+    G = K // g
+    wd, sd = w.to(dev), s.to(dev)
+    q = torch.full((C, K), 77, dtype=torch.int32, device=dev) if unpacked else None
+    qp = torch.full((C, K // 8), 77, dtype=torch.int32, device=dev) if packed else None
+    sc = torch.zeros((C, G), dtype=torch.float16, device=dev)
+    zp = torch.full((C, G), 77, dtype=torch.int32, device=dev) if want_zp else None
+    zq = torch.full((C, -(-G // 8)), 77, dtype=torch.int32, device=dev) if want_zq else None
+    rc = L.awqk_group_quant(wd.data_ptr(), N.dtype_code(w.dtype), C, K, g, 4, int(sym), N.ARITH_FP32,
+                            N.ptr(q), N.ptr(qp), sc.data_ptr(), N.ptr(zp), N.ptr(zq), sd.data_ptr(), None)
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    return {"tensor_q": q, "qweight": qp, "scales": sc, "zero_points": zp, "qzeros": zq}
+
+
+def _check(got, want, what):
+    for k, v in got.items():
+        if v is not None:
+            assert_same(v.cpu(), want[k], f"{what}/{k}")
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("sym", [False, True])
+@pytest.mark.parametrize("g", [32, 64, 128])
+def test_colscale_slab_kernel_bit_exact(native_lib, cuda_device, dt, sym, g):
+    from awq_quantizer import _native as N
+    for C, K in ((1, 1024), (8, 1024), (13, 2048), (300, 4096), (77, 3072)):
+        w = datagen.weights((C, K), dt, datagen.seed_of("cs", C, K, dt))
+        s = _scales(K, C + K)
+        want = O.pack_result(O.quantize_scaled(w, s, 4, g, sym))
+        _check(_run(native_lib, N, w, s, g, sym, cuda_device), want, f"{C}x{K}")
+        _check(_run(native_lib, N, w, s, g, sym, cuda_device, unpacked=False), want, f"{C}x{K}/packed only")
+        _check(_run(native_lib, N, w, s, g, sym, cuda_device, packed=False, want_zq=False), want, f"{C}x{K}/unpacked only")
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_colscale_special_values(native_lib, cuda_device, sym):
+    """slow-path groups inside the slab kernel: non-finite values, constant / all-zero groups, huge and tiny
+    magnitudes, all-positive rows (clamped zero point), scales spanning 2^-20 .. 2^20"""
+    from awq_quantizer import _native as N
+    C, K, g = 24, 2048, 128
+    w = datagen.weights((C, K), "bf16", 99).float()
+    w[0, :128] = 0.0
+    w[1, 128:256] = 0.5
+    w[2, 5] = float("nan")
+    w[3, 300] = float("inf")
+    w[4, 700] = float("-inf")
+    w[5] *= 1e30
+    w[6] *= 1e-30
+    w[7] = w[7].abs() + 0.25
+    w[8] = -w[8].abs() - 0.25
+    w[9, 1024:1152] = torch.linspace(-1, 1, 128)
+    w[10, :] = 3.0e38
+    w = w.to(torch.bfloat16)
+    s = _scales(K, 5)
+    s[::7] = 2.0 ** -20
+    s[3::11] = 2.0 ** 20
+    want = O.pack_result(O.quantize_scaled(w, s, 4, g, sym))
+    _check(_run(native_lib, N, w, s, g, sym, cuda_device), want, "special")
+
+
+def test_colscale_many_row_blocks_and_canaries(native_lib, cuda_device):
+    """more row blocks than CTAs per slab (several pipeline iterations per CTA), ragged last row block,
+    guarded output buffers"""
+    from awq_quantizer import _native as N
+    from tests.test_gpu_parity import _canaries_intact, _guarded
+    dev = cuda_device
+    C, K, g = 8 * 700 + 3, 1024, 128
+    G = K // g
+    w = datagen.weights((C, K), "bf16", 17)
+    s = _scales(K, 3)
+    want = O.pack_result(O.quantize_scaled(w, s, 4, g, False))
+    sizes = {"q": C * K * 4, "qp": C * K // 2, "s": C * G * 2, "z": C * G * 4, "zq": C * (G // 8) * 4}
+    bufs = {k: _guarded(v, dev) for k, v in sizes.items()}
+    wd, sd = w.to(dev), s.to(dev)
+    rc = native_lib.awqk_group_quant(wd.data_ptr(), N.BF16, C, K, g, 4, 0, N.ARITH_FP32, bufs["q"][1].data_ptr(),
+                                     bufs["qp"][1].data_ptr(), bufs["s"][1].data_ptr(), bufs["z"][1].data_ptr(),
+                                     bufs["zq"][1].data_ptr(), sd.data_ptr(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    for k, (b, _) in bufs.items():
+        assert _canaries_intact(b, sizes[k]), k
+    assert_same(bufs["q"][1].view(torch.int32).reshape(C, K).cpu(), want["tensor_q"], "q")
+    assert_same(bufs["qp"][1].view(torch.int32).reshape(C, K // 8).cpu(), want["qweight"], "qweight")
+    assert_same(bufs["s"][1].view(torch.float16).reshape(C, G).cpu(), want["scales"], "scales")
+    assert_same(bufs["z"][1].view(torch.int32).reshape(C, G).cpu(), want["zero_points"], "zp")
+    assert_same(bufs["zq"][1].view(torch.int32).reshape(C, G // 8).cpu(), want["qzeros"], "qzeros")
+
+
+def test_colscale_matches_register_path(native_lib, cuda_device, monkeypatch):
+    """the slab kernel and the register-path kernel (K not a multiple of 1024 -> group_quant_flat) agree
+    on the shared left part of a matrix whose column scales are equal there"""
+    from awq_quantizer import _native as N
+    C, g = 64, 128
+    w = datagen.weights((C, 2048), "bf16", 123)
+    s = _scales(2048, 9)
+    a = _run(native_lib, N, w, s, g, False, cuda_device)                                   # slab kernel
+    b = _run(native_lib, N, w[:, :1536].contiguous(), s[:1536].contiguous(), g, False, cuda_device)   # register path
+    assert torch.equal(a["tensor_q"][:, :1536], b["tensor_q"])
+    assert torch.equal(a["scales"][:, :12], b["scales"])
+    assert torch.equal(a["zero_points"][:, :12], b["zero_points"])
