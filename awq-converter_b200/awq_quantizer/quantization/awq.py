@@ -232,9 +232,9 @@ class AWQQuantizer:
                         and pipe_eligible(tuple(t.shape), t.dtype, self.group_size, self.bits)}
                 if flat:
                     try:
-                        res = quantize_arena(HostArena.from_tensors(flat), bits=self.bits, group_size=self.group_size,
+                        res = quantize_arena(HostArena.for_tensors(flat), bits=self.bits, group_size=self.group_size,
                                              symmetric=self.symmetric, arith=self.arith, device=dev,
-                                             chunk_bytes=chunk_bytes, packed=False, unpacked=True)
+                                             chunk_bytes=chunk_bytes, packed=False, unpacked=True, sources=flat)
                         for name in flat:
                             self.logger.info(f"Successfully quantized tensor: {name}")
                         quantized.update(res)
@@ -268,11 +268,12 @@ class AWQQuantizer:
                     flat[name] = t
                 else:
                     singles[name] = t
-            arena = HostArena.from_tensors(flat) if flat else None
+            arena = HostArena.for_tensors(flat) if flat else None
         if arena is not None:
             quantized.update(quantize_arena(arena, bits=self.bits, group_size=self.group_size,
                                             symmetric=self.symmetric, arith=self.arith, device=dev,
-                                            chunk_bytes=chunk_bytes, sync=False))
+                                            chunk_bytes=chunk_bytes, sync=False,
+                                            sources=None if isinstance(tensors, HostArena) else flat))
         rest = {}
         for name, tensor in singles.items():           # rows of whole groups: same pipeline, chunked by rows
             if isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu" and \

@@ -181,6 +181,9 @@ constexpr int kV2UnpStageBytes = kV2ConsumerWarps * kV2WarpTile * 4;   // 32 KiB
 // (8 bulk copies of 2 KiB, one per consumer warp), so a thread's 32 columns never change and their
 // scales live in registers for the whole kernel.  Requires K % 1024 == 0: every output offset is then
 // still (thread base) + it * (constant stride) in the flat row-major arrays, exactly as in the flat mode.
+// The cps CTAs of a slab take row blocks j, j + cps, ...: all slabs sweep the same rows at the same time,
+// which keeps the HBM pages of a row open (a contiguous, perfectly balanced split of the row blocks per
+// CTA measured 3-8 % slower for that reason).
 struct V2ColScale {
   const float* s;     // [K]
   int64_t K, C;

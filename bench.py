@@ -344,7 +344,7 @@ def run_native(args):
     e2e_val = total_payload / (dt / e2e_steps) / 1e9
     # the unchanged reference call -- quantize_model(dict) -> int32 tensor_q / fp16 scales / int32 zero points --
     # for the record (D2H of 4 B per element makes it PCIe-bound at ~1/4 of the packed path)
-    host_dict = {n: arena.views[n] for n in flat}
+    host_dict = {n: arena.views[n].clone() for n in flat}      # ordinary pageable tensors, as a loader returns them
     host_dict.update(h_single)
     qz.quantize_model(host_dict)
     torch.cuda.synchronize(dev)

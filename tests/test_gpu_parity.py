@@ -474,3 +474,25 @@ def test_default_quantize_model_is_pipelined_and_reference_exact(native_lib, cud
         loop = qz.quantize_model(tensors, pipeline=False)
         for n in out:
             assert_quant_equal(out[n], loop[n], n + "/loop")
+
+
+@pytest.mark.parametrize("segment_bytes", [1 << 14, 48 << 10, 1 << 20])
+def test_arena_staged_from_pageable_tensors(native_lib, cuda_device, segment_bytes):
+    """quantize_arena(sources=...): the arena is filled segment by segment while the pipeline already runs on
+    the previous segment -- segment ends inside tensors, at tensor ends and across tile padding"""
+    from awq_quantizer.quantization.arena import HostArena, quantize_arena
+    shapes = {"a": (24, 1024), "b": (1024,), "c": (40, 2048), "d": (8, 3, 1024), "e": (3, 1024), "h": (16, 1024)}
+    tensors = {n: datagen.weights(s, "fp16" if n == "h" else "bf16", datagen.seed_of("stage", n)) for n, s in shapes.items()}
+    arena = HostArena.for_tensors(tensors)
+    for dt, buf in arena.buffers.items():           # poison the slots: stale data must never reach the GPU
+        buf.view(torch.int16)[:] = 0x7FC1
+    for name, off, n in [x for lay in arena.layout.values() for x in lay]:
+        dt = arena.specs[name][1]
+        arena.buffers[dt][off + n:off + (n + 8191) // 8192 * 8192].zero_()
+    res = quantize_arena(arena, bits=4, group_size=128, symmetric=False, arith="native", device=cuda_device,
+                         chunk_bytes=1 << 16, packed=True, unpacked=True, want_zero_points=True, sources=tensors,
+                         segment_bytes=segment_bytes)
+    for n, t in tensors.items():
+        want = O.pack_result(O.group_quant_vec(t, 4, 128, False, True))
+        assert_quant_equal(res[n], want, n, keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
+        assert torch.equal(arena.views[n], t)
