@@ -451,7 +451,7 @@ static int launch_generic(const InT* w, int64_t C, int64_t K, int g, int64_t G, 
 // awqk_group_quant_tma.cu
 int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, bool sym, int arith,
                            uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
-                           cudaStream_t st);
+                           int zq_log2, cudaStream_t st);
 
 bool group_quant_tma_cs_eligible(int64_t C, int64_t K);
 int launch_group_quant_tma_cs(const void* w, int dtype, int64_t C, int64_t K, int g, bool sym, const float* col_scale,
@@ -502,7 +502,12 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
   QuantOut out{q_unpacked, q_packed, reinterpret_cast<__half*>(scales_f16), zp, zp_packed};
 
   if (path == 1) {
-    const bool flat_zp = (G % per) == 0;
+    const bool tma_plain = bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) &&
+                           (q_packed != nullptr || q_unpacked != nullptr) && col_scale == nullptr && tma_path_enabled() &&
+                           (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0;
+    // rows of 1 / 2 / 4 groups: K1 v2 writes one zero-padded word per row itself
+    const int zq_log2 = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : 3;
+    const bool flat_zp = (G % per) == 0 || (tma_plain && zq_log2 < 3);
     int32_t* zp_for_pack = zp;
     if (zp_packed != nullptr && !flat_zp) {
       if (zp == nullptr) return AWQK_E_WORKSPACE;  // row-wise zero packing needs the int32 zeros
@@ -510,11 +515,10 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
     }
     const int64_t n = C * K;
     int rc;
-    if (bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) && (q_packed != nullptr || q_unpacked != nullptr) &&
-        col_scale == nullptr && tma_path_enabled() && (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0) {
+    if (tma_plain) {
       // K1 v2: TMA-staged, packed-math kernel (int4 pack path and the reference's int32 code layout)
       rc = launch_group_quant_tma(w, dtype, n, group_size, sym, arith, q_packed, q_unpacked, scales_f16, zp,
-                                  out.zp_packed, st);
+                                  out.zp_packed, zq_log2, st);
     } else if (bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) && (q_packed != nullptr || q_unpacked != nullptr) &&
                col_scale != nullptr && tma_path_enabled() && (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0 &&
                group_quant_tma_cs_eligible(C, K)) {

@@ -168,6 +168,8 @@ struct V2Out {
   __half* scales;
   int32_t* zp;          // nullable
   uint32_t* zp_packed;  // nullable (flat layout only)
+  int zq_log2;          // log2(groups per packed zero-point word): 3 = eight consecutive groups of the flat
+                        // layout; 0/1/2 = rows of 1/2/4 groups, one zero-padded word per row ([C, 1] qzeros)
 };
 
 // UNPACKED: additionally emits the reference's int32 code tensor (awq.py:329, 4 B per element).  The 32
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kV2Threads, (UNPACKED || CS) ? 2 : 3)
 group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out, V2ColScale csp) {
   static_assert(!CS || A == AR_F32, "column scaling is defined in fp32 arithmetic");
   constexpr int LPG = G / 32;            // lanes per group (4, 2, 1)
-  constexpr int LPW = 8 * LPG;           // lanes per packed zero-point word (32, 16, 8)
+  const int LPW = LPG << out.zq_log2;    // lanes per packed zero-point word (8 groups: 32, 16, 8)
   constexpr int QMIN = SYM ? -8 : 0;
   constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + 15);
 
@@ -296,15 +298,15 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   uint8_t* const q_base = reinterpret_cast<uint8_t*>(out.q_packed + (e_first >> 3));
   uint8_t* const s_base = reinterpret_cast<uint8_t*>(out.scales + e_first / G);
   uint8_t* const z_base = reinterpret_cast<uint8_t*>(out.zp + e_first / G);
-  uint8_t* const zq_base = reinterpret_cast<uint8_t*>(out.zp_packed + e_first / (8 * G));
+  uint8_t* const zq_base = reinterpret_cast<uint8_t*>(out.zp_packed + ((e_first / G) >> out.zq_log2));
   const uint32_t q_step = (uint32_t)(e_stride >> 3) * 4u;          // bytes per iteration (< 2^32: grid <= 3*SMs)
   const uint32_t s_step = (uint32_t)(e_stride / G) * 2u;
   const uint32_t z_step = (uint32_t)(e_stride / G) * 4u;
-  const uint32_t zq_step = (uint32_t)(e_stride / (8 * G)) * 4u;
+  const uint32_t zq_step = (uint32_t)((e_stride / G) >> out.zq_log2) * 4u;
   const bool has_zp = out.zp != nullptr, has_zq = out.zp_packed != nullptr;
   const bool leader = (lane % LPG) == 0;
-  const bool zq_writer = (lane % LPW) == 0;
-  const uint32_t zq_shift = 4u * ((uint32_t)(lane / LPG) & 7u);
+  const bool zq_writer = (lane & (LPW - 1)) == 0;
+  const uint32_t zq_shift = 4u * ((uint32_t)(lane / LPG) & ((1u << out.zq_log2) - 1u));
   const uint32_t zq_mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
 
   // UNPACKED: warp-private staging of 256 x 16 B chunks.  Thread l owns logical chunks 8l..8l+7 (4 codes
@@ -557,11 +559,12 @@ static int launch_v2_g(const InT* w, int64_t n, int g, bool sym, V2Out out, V2Co
 }
 
 // Entry used by awqk_group_quant: int4, bf16/fp16 input, flat layout (K % g == 0, g in {32,64,128},
-// 16-byte aligned base).  zp_packed must be null unless G % 8 == 0.
+// 16-byte aligned base).  zp_packed: zq_log2 = 3 when a row is a whole number of 8-group words (G % 8 == 0),
+// 0/1/2 when a row is 1/2/4 groups (one word per row); otherwise it must be null.
 int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, bool sym, int arith,
                            uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
-                           cudaStream_t st) {
-  V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed};
+                           int zq_log2, cudaStream_t st) {
+  V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed, zq_log2};
   const V2ColScale none{nullptr, 0, 0, 0, 0};
   if (dtype == AWQK_BF16) {
     auto p = reinterpret_cast<const __nv_bfloat16*>(w);
@@ -583,7 +586,7 @@ bool group_quant_tma_cs_eligible(int64_t C, int64_t K) {
 int launch_group_quant_tma_cs(const void* w, int dtype, int64_t C, int64_t K, int g, bool sym, const float* col_scale,
                               uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                               cudaStream_t st) {
-  V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed};
+  V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed, 3};
   const V2ColScale csp{col_scale, K, C, 0, 0};
   if (dtype == AWQK_BF16)
     return launch_v2_g<__nv_bfloat16, AR_F32, true>(reinterpret_cast<const __nv_bfloat16*>(w), C * K, g, sym, out, csp, st);

@@ -234,26 +234,24 @@ def run_native(args):
                          torch.empty((C, G), dtype=torch.int32, device=dev),
                          torch.empty((C, -(-G // per)), dtype=torch.int32, device=dev))
     arith = N.ARITH_FP32 if args.arith == "fp32" else N.ARITH_NATIVE
-    launches_per_step = 1 + 2 * len(d_single)
+    # a row-mode tensor is one K1 launch when its rows are 1 / 2 / 4 groups (zero words packed in the kernel),
+    # else K1 + pack_zeros_rows
+    launches_per_step = 1 + sum(1 if (bits == 4 and v[1] // g in (1, 2, 4)) else 2 for v in single_out.values())
 
     def k1_arena():
         st = torch.cuda.current_stream(dev).cuda_stream
         N.check(L.awqk_group_quant(d_arena.data_ptr(), N.BF16, 1, n_arena, g, bits, int(sym), arith, None,
                                    d_q.data_ptr(), d_s.data_ptr(), None, d_zq.data_ptr(), None, st))
 
-    side_stream = torch.cuda.Stream(dev)
-
     def step_launches():
-        # the row-mode tensors run on a forked stream: their ramp-up overlaps the arena kernel's tail
-        cur = torch.cuda.current_stream(dev)
-        side_stream.wait_stream(cur)
-        k1_arena()
-        st = side_stream.cuda_stream
+        # the (small) row-mode tensors first, then the arena: one stream, no fork / join.  (A forked stream
+        # buys nothing: the persistent arena kernel fills every SM, so the small kernels would only run at its tail.)
+        st = torch.cuda.current_stream(dev).cuda_stream
         for n, t in d_single.items():
             C, K, qw, sc, zp, zq = single_out[n]
             N.check(L.awqk_group_quant(t.data_ptr(), N.BF16, C, K, g, bits, int(sym), arith, None, qw.data_ptr(),
-                                       sc.data_ptr(), zp.data_ptr(), zq.data_ptr(), None, st))
-        cur.wait_stream(side_stream)
+                                       sc.data_ptr(), None if (bits == 4 and K // g in (1, 2, 4)) else zp.data_ptr(), zq.data_ptr(), None, st))
+        k1_arena()
 
     # one pass = one CUDA graph launch (the per-tensor launches are captured once, replayed per step)
     step_device, graph_mode = step_launches, "direct launches"

@@ -496,3 +496,27 @@ def test_arena_staged_from_pageable_tensors(native_lib, cuda_device, segment_byt
         want = O.pack_result(O.group_quant_vec(t, 4, 128, False, True))
         assert_quant_equal(res[n], want, n, keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
         assert torch.equal(arena.views[n], t)
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+def test_rows_of_1_2_4_groups_pack_zero_words_in_kernel(native_lib, cuda_device, dt):
+    """K = 1, 2 or 4 groups: K1 v2 writes the row-padded qzeros word itself (no int32 zero points needed, no
+    second kernel); compared with the oracle's per-row packing"""
+    from awq_quantizer import _native as N
+    for (C, K), g in (((72, 512), 128), ((9, 256), 128), ((33, 128), 128), ((40, 128), 32), ((8, 64), 32), ((5, 32), 32),
+                      ((130, 256), 64)):
+        for sym in (False, True):
+            w = datagen.weights((C, K), dt, datagen.seed_of("rowzp", C, K, g), offset=0.01)
+            G = K // g
+            wd = w.to(cuda_device)
+            qp = torch.full((C, K // 8), 5, dtype=torch.int32, device=cuda_device)
+            sc = torch.zeros((C, G), dtype=torch.float16, device=cuda_device)
+            zq = torch.full((C, 1), 5, dtype=torch.int32, device=cuda_device)
+            rc = native_lib.awqk_group_quant(wd.data_ptr(), N.dtype_code(w.dtype), C, K, g, 4, int(sym), N.ARITH_NATIVE,
+                                             None, qp.data_ptr(), sc.data_ptr(), None, zq.data_ptr(), None, None)
+            assert rc == 0, (rc, C, K, g)
+            torch.cuda.synchronize()
+            want = O.pack_result(O.group_quant_vec(w, 4, g, sym, True))
+            assert_same(qp.cpu(), want["qweight"], f"{C}x{K}/g{g}/qweight")
+            assert_same(sc.cpu(), want["scales"], f"{C}x{K}/g{g}/scales")
+            assert_same(zq.cpu(), want["qzeros"], f"{C}x{K}/g{g}/qzeros")
