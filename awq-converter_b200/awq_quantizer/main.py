@@ -274,7 +274,8 @@ def main(argv=None) -> int:
             done: Dict[str, dict] = {}
             searched = {n: t for n, t in shard.items() if n in calib and t.dim() == 2}
             if searched:
-                done.update(qz.quantize_model(searched, activations={n: calib[n] for n in searched}, pack=args.pack))
+                done.update(qz.quantize_model(searched, activations={n: calib[n] for n in searched}, pack=args.pack,
+                                              keep_unpacked=True))
                 shard = {n: t for n, t in shard.items() if n not in done}
             batches = prepare_tensors_for_quantization(shard, device, args.max_memory, args.batch_size, logger)
             with ThreadPoolExecutor(max_workers=max(1, args.num_workers)) as ex:

@@ -195,7 +195,7 @@ class AWQQuantizer:
 
     # ------------------------------------------------------------------ awq.py:435-457
     def quantize_model(self, tensors, *, pack: bool = False, chunk_bytes: int = 32 << 20, pipeline: bool = True,
-                       activations: Optional[Dict[str, torch.Tensor]] = None):
+                       activations: Optional[Dict[str, torch.Tensor]] = None, keep_unpacked: Optional[bool] = None):
         """dict-in / dict-out; a tensor that raises is logged and skipped (awq.py:453-455).
 
         ``pack=False`` (default): the reference's result layout per tensor (``tensor_q`` int32, ``scales``
@@ -207,7 +207,9 @@ class AWQQuantizer:
         ``tensors`` may already be a ``HostArena`` (zero-copy).
 
         ``activations`` (name -> calibration activations [tokens, in_features]) turns on the activation-aware
-        alpha search for those tensors (quantization/search.py); all other tensors take the paths above."""
+        alpha search for those tensors (quantization/search.py: streamed upload / search / download); all
+        other tensors take the paths above.  With ``pack`` the searched results carry ``tensor_q`` only if
+        ``keep_unpacked`` is true (4 bytes per element over PCIe), like the packed path."""
         if activations:
             from .search import quantize_model_with_search
             dev = self._cuda_device()
@@ -215,7 +217,7 @@ class AWQQuantizer:
             searched = {}
             try:
                 searched = quantize_model_with_search(self, {n: t for n, t in tensors.items() if n in activations},
-                                                      activations, dev, pack=pack)
+                                                      activations, dev, pack=pack, keep_unpacked=keep_unpacked)
             except Exception as e:
                 self.logger.error(f"Activation-aware search failed: {e}")
             rest = {n: t for n, t in tensors.items() if n not in searched}

@@ -210,13 +210,47 @@ def test_quantize_model_with_activations(native_lib, cuda_device):
     acts = {"q_proj": X1, "k_proj": X1, "down": X2}
     qz = AWQQuantizer(bits=4, group_size=128, symmetric=False, device="cuda:0", logger_level="ERROR", n_grid=10)
     out = qz.quantize_model(tensors, activations=acts, pack=True, )
+    both = qz.quantize_model(tensors, activations=acts, pack=True, keep_unpacked=True)
+    plain = qz.quantize_model(tensors, activations=acts)
     assert list(out) == list(tensors)
     for n in acts:
         single = qz.quantize(tensors[n], activations=acts[n], pack=True)
         assert int(out[n]["best_idx"]) == int(single["best_idx"])
+        assert abs(float(out[n]["alpha"]) - float(single["alpha"])) == 0
         assert torch.equal(out[n]["awq_scale"], single["awq_scale"])
-        assert_quant_equal(out[n], single, n, keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
+        assert "tensor_q" not in out[n] and "qweight" not in plain[n]      # packed results skip the 4 B/element codes
+        assert_quant_equal(out[n], single, n, keys=("scales", "zero_points", "qweight", "qzeros"))
+        assert_quant_equal(both[n], single, n, keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
+        assert_quant_equal(plain[n], single, n, keys=("tensor_q", "scales", "zero_points"))
         assert torch.allclose(out[n]["search_err"], single["search_err"], rtol=1e-9)
     want = O.pack_result(O.group_quant_vec(tensors["norm"], 4, 128, False, True))
     assert_same(out["norm"]["qweight"], want["qweight"], "norm")
     assert "awq_scale" not in out["norm"]
+
+
+def test_streamed_model_search_many_waves(native_lib, cuda_device):
+    """quantize_model_with_search with waves far smaller than the model: slot reuse in the uploader (pinned
+    staging + device slots), pageable / pinned / device-resident inputs mixed, results identical to the
+    one-tensor API"""
+    from awq_quantizer.quantization import AWQQuantizer
+    from awq_quantizer.quantization.search import quantize_model_with_search
+    X = {256: datagen.activations(96, 256, "bf16", 1), 512: datagen.activations(64, 512, "bf16", 2)}
+    shapes = [(64, 256), (128, 512), (32, 256), (96, 512), (64, 512), (16, 256), (48, 256), (8, 512), (72, 256)]
+    tensors, acts = {}, {}
+    for i, s in enumerate(shapes):
+        w = datagen.weights(s, "fp16" if i == 4 else "bf16", 100 + i)
+        if i % 3 == 1:
+            w = w.pin_memory()
+        elif i % 3 == 2:
+            w = w.to(cuda_device)
+        tensors[f"t{i}"] = w
+        acts[f"t{i}"] = X[s[1]]
+    qz = AWQQuantizer(bits=4, group_size=128, symmetric=False, device="cuda:0", logger_level="ERROR", n_grid=6)
+    for wave_bytes in (1, 70_000, 1 << 30):
+        out = quantize_model_with_search(qz, tensors, acts, cuda_device, pack=True, wave_bytes=wave_bytes)
+        assert list(out) == list(tensors)
+        for n, w in tensors.items():
+            single = qz.quantize(w.cpu(), activations=acts[n], pack=True)
+            assert int(out[n]["best_idx"]) == int(single["best_idx"]), (n, wave_bytes)
+            assert_quant_equal(out[n], single, f"{n}/{wave_bytes}", keys=("scales", "zero_points", "qweight", "qzeros"))
+            assert out[n]["qweight"].device.type == "cpu" and out[n]["qweight"].is_pinned()
