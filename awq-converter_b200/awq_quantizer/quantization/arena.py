@@ -54,9 +54,10 @@ class HostArena:
     ``specs``: name -> (shape, dtype).  ``views[name]`` is a tensor view into the arena: a loader can
     read file bytes straight into it (zero copy), or ``from_tensors`` copies existing tensors in."""
 
-    def __init__(self, specs: Dict[str, Tuple[tuple, torch.dtype]], pin: bool = True):
+    def __init__(self, specs: Dict[str, Tuple[tuple, torch.dtype]], pin: bool = True, allocate: bool = True):
         """Allocates the buffers; only the tile padding behind each slot is zeroed (the slots themselves are
-        about to be overwritten by the caller, and a memset of the whole model is a wasted pass over DRAM)."""
+        about to be overwritten by the caller, and a memset of the whole model is a wasted pass over DRAM).
+        ``allocate=False``: layout only (the virtual arena of awqk_pipe_quant_gather)."""
         self.specs = dict(specs)
         self.layout: Dict[torch.dtype, List[Tuple[str, int, int]]] = {}   # dtype -> [(name, offset, numel)]
         self.buffers: Dict[torch.dtype, torch.Tensor] = {}
@@ -67,6 +68,9 @@ class HostArena:
             off = sizes.get(dtype, 0)
             self.layout.setdefault(dtype, []).append((name, off, n))
             sizes[dtype] = off + (n + TILE - 1) // TILE * TILE
+        self.sizes = sizes
+        if not allocate:
+            return
         for dtype, total in sizes.items():
             buf = torch.empty(total, dtype=dtype, pin_memory=pin and torch.cuda.is_available())
             self.buffers[dtype] = buf
@@ -83,9 +87,9 @@ class HostArena:
 
     @classmethod
     def for_tensors(cls, tensors: Dict[str, torch.Tensor], pin: bool = True) -> "HostArena":
-        """layout only: the slots are filled later (quantize_arena(..., sources=tensors) stages them segment
-        by segment while the GPU pipeline already works on the previous segment)"""
-        return cls({k: (tuple(v.shape), v.dtype) for k, v in tensors.items()}, pin=pin)
+        """layout only -- a virtual arena: quantize_arena(..., sources=tensors) lets the native pipeline gather
+        the tensors from where they are (pageable memory) through its own bounded ring of pinned buffers"""
+        return cls({k: (tuple(v.shape), v.dtype) for k, v in tensors.items()}, pin=pin, allocate=False)
 
     def nbytes(self) -> int:
         return sum(b.numel() * b.element_size() for b in self.buffers.values())
@@ -115,12 +119,14 @@ def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: b
                    device: torch.device, chunk_bytes: int = 32 << 20, want_zero_points: bool = False,
                    out: Optional[dict] = None, sync: bool = True, packed: bool = True,
                    unpacked: bool = False, sources: Optional[Dict[str, torch.Tensor]] = None,
-                   segment_bytes: int = 64 << 20) -> Dict[str, Dict[str, torch.Tensor]]:
+                   pin_results: bool = True) -> Dict[str, Dict[str, torch.Tensor]]:
     """Quantize every tensor of ``arena`` through the chunked H2D -> K1 -> D2H pipeline.
 
-    ``sources`` (name -> CPU tensor): the arena is still empty; its slots are filled from these tensors in
-    layout order, ``segment_bytes`` at a time, and every filled segment is handed to the (asynchronous)
-    pipeline at once -- the host-side staging copy of segment i+1 overlaps the transfers of segment i.
+    ``sources`` (name -> CPU tensor): the arena is virtual (``HostArena.for_tensors``); the native pipeline
+    (awqk_pipe_quant_gather) gathers the tensors chunk by chunk through its own pinned bounce ring and drains
+    the results into ordinary (pageable) host arrays -- no pinned allocation proportional to the model
+    (cudaHostAlloc runs at ~2.3 GB/s, 20x slower than the pipeline itself), blocking.  With ``pin_results``
+    the result arrays are pinned and written by the D2H copies directly (worth it when the allocation is re-used).
 
     ``packed``   -> 'qweight' / 'qzeros' (+ 'scales'), ``unpacked`` -> the reference's 'tensor_q' int32 /
     'zero_points' int32 (+ 'scales').  The tensors are views of pinned host output arenas (``out`` may
@@ -131,11 +137,12 @@ def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: b
     results: Dict[str, Dict[str, torch.Tensor]] = {}
     outs = out if out is not None else {}
     want_z = want_zero_points or unpacked
-    for dtype, buf in arena.buffers.items():
-        n = buf.numel()
-        key = (dtype, n, bits, group_size, want_z, packed, unpacked)
+    for dtype in arena.layout:
+        buf = arena.buffers.get(dtype)
+        n = arena.sizes[dtype]
+        pin = torch.cuda.is_available() and (sources is None or pin_results)
+        key = (dtype, n, bits, group_size, want_z, packed, unpacked, pin)
         if key not in outs:
-            pin = torch.cuda.is_available()
             outs[key] = {
                 "q": torch.empty(n // per, dtype=torch.int32, pin_memory=pin) if packed else None,
                 "s": torch.empty(n // group_size, dtype=torch.float16, pin_memory=pin),
@@ -144,40 +151,20 @@ def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: b
                 "tq": torch.empty(n, dtype=torch.int32, pin_memory=pin) if unpacked else None,
             }
         o = outs[key]
-        esz = buf.element_size()
-
-        def submit(e0: int, e1: int) -> None:
-            """elements [e0, e1) of this buffer (tile aligned) -> pipeline; returns once everything is enqueued"""
-            def at(t, div, size):
-                return None if t is None else t.data_ptr() + (e0 // div) * size
-            N.check(L.awqk_pipe_quant_host(pipe, buf.data_ptr() + e0 * esz, N.dtype_code(dtype), 1, e1 - e0, group_size,
-                                           bits, int(symmetric), N.ARITH_FP32 if arith == "fp32" else N.ARITH_NATIVE,
-                                           at(o["tq"], 1, 4), at(o["q"], per, 4), at(o["s"], group_size, 2),
-                                           at(o["z"], group_size, 4), at(o["zq"], group_size * per, 4)),
-                    "awqk_pipe_quant_host")
-
+        ar = N.ARITH_FP32 if arith == "fp32" else N.ARITH_NATIVE
         if sources is None:
-            submit(0, n)
+            N.check(L.awqk_pipe_quant_host(pipe, buf.data_ptr(), N.dtype_code(dtype), 1, n, group_size, bits,
+                                           int(symmetric), ar, N.ptr(o["tq"]), N.ptr(o["q"]), o["s"].data_ptr(),
+                                           N.ptr(o["z"]), N.ptr(o["zq"])), "awqk_pipe_quant_host")
         else:
-            seg_elems = max(TILE, segment_bytes // esz // TILE * TILE)
-            flat = buf
-            done = 0                                   # everything below `done` has been submitted
-            for name, off, numel in arena.layout[dtype]:
-                src = sources[name].detach().contiguous().view(-1)
-                end = off + (numel + TILE - 1) // TILE * TILE
-                pos = 0
-                while pos < numel:
-                    take = min(numel - pos, seg_elems - (off + pos - done))
-                    flat[off + pos:off + pos + take].copy_(src[pos:pos + take])
-                    pos += take
-                    if off + pos - done >= seg_elems and pos < numel:
-                        submit(done, off + pos)        # off + pos - done == seg_elems: tile aligned
-                        done = off + pos
-                if end - done >= seg_elems:
-                    submit(done, end)
-                    done = end
-            if done < n:
-                submit(done, n)
+            lay = arena.layout[dtype]
+            keep = [sources[name].detach().contiguous() for name, _, _ in lay]     # alive during the call
+            ptrs = (C.c_void_p * len(lay))(*[t.data_ptr() for t in keep])
+            nums = (C.c_int64 * len(lay))(*[numel for _, _, numel in lay])
+            N.check(L.awqk_pipe_quant_gather(pipe, len(lay), ptrs, nums, N.dtype_code(dtype), group_size, bits,
+                                             int(symmetric), ar, N.ptr(o["tq"]), N.ptr(o["q"]), o["s"].data_ptr(),
+                                             N.ptr(o["z"]), N.ptr(o["zq"])), "awqk_pipe_quant_gather")
+            del keep
         for name, off, numel in arena.layout[dtype]:
             shape = arena.specs[name][0]
             rows = 1 if len(shape) <= 1 else shape[0]

@@ -49,6 +49,7 @@ class AWQQuantizer:
         *,
         arith: str = "native",
         n_grid: int = 20,
+        pin_results: Optional[bool] = None,
     ):
         self.bits = bits
         self.group_size = group_size
@@ -59,6 +60,12 @@ class AWQQuantizer:
         self.per_channel = per_channel
         self.arith = arith
         self.n_grid = n_grid
+        # quantize_model() results in page-locked host memory?  Pinning runs at ~2.3 GB/s (20x slower than the
+        # pipeline), so it only pays when the allocation is re-used.  None = adaptive: the first model of this
+        # quantizer gets ordinary (pageable) results drained through the pipeline's bounded pinned ring, later
+        # models get pinned results straight from the D2H copies (torch's pinned allocator caches the blocks).
+        self.pin_results = pin_results
+        self._models_done = 0
         # awq.py:70-73: default device is CUDA.  (No silent CPU downgrade here.)
         self.device = "cuda" if device is None else device
         self.logger = get_logger(name=logger_name, level=logger_level, to_file=logger_to_file,
@@ -193,9 +200,15 @@ class AWQQuantizer:
             out["qzeros"] = qzeros
         return out
 
+    def _pin_now(self) -> bool:
+        pin = self._models_done > 0 if self.pin_results is None else bool(self.pin_results)
+        self._models_done += 1
+        return pin
+
     # ------------------------------------------------------------------ awq.py:435-457
     def quantize_model(self, tensors, *, pack: bool = False, chunk_bytes: int = 32 << 20, pipeline: bool = True,
-                       activations: Optional[Dict[str, torch.Tensor]] = None, keep_unpacked: Optional[bool] = None):
+                       activations: Optional[Dict[str, torch.Tensor]] = None, keep_unpacked: Optional[bool] = None,
+                       _pin: Optional[bool] = None):
         """dict-in / dict-out; a tensor that raises is logged and skipped (awq.py:453-455).
 
         ``pack=False`` (default): the reference's result layout per tensor (``tensor_q`` int32, ``scales``
@@ -210,6 +223,7 @@ class AWQQuantizer:
         alpha search for those tensors (quantization/search.py: streamed upload / search / download); all
         other tensors take the paths above.  With ``pack`` the searched results carry ``tensor_q`` only if
         ``keep_unpacked`` is true (4 bytes per element over PCIe), like the packed path."""
+        pin = self._pin_now() if _pin is None else _pin          # one decision per model
         if activations:
             from .search import quantize_model_with_search
             dev = self._cuda_device()
@@ -217,11 +231,12 @@ class AWQQuantizer:
             searched = {}
             try:
                 searched = quantize_model_with_search(self, {n: t for n, t in tensors.items() if n in activations},
-                                                      activations, dev, pack=pack, keep_unpacked=keep_unpacked)
+                                                      activations, dev, pack=pack, keep_unpacked=keep_unpacked,
+                                                      pin_results=pin)
             except Exception as e:
                 self.logger.error(f"Activation-aware search failed: {e}")
             rest = {n: t for n, t in tensors.items() if n not in searched}
-            other = self.quantize_model(rest, pack=pack, chunk_bytes=chunk_bytes, pipeline=pipeline) if rest else {}
+            other = self.quantize_model(rest, pack=pack, chunk_bytes=chunk_bytes, pipeline=pipeline, _pin=pin) if rest else {}
             return {n: (searched[n] if n in searched else other[n]) for n in tensors if n in searched or n in other}
         if not pack:
             from .arena import HostArena, pipe_eligible, quantize_arena
@@ -236,7 +251,8 @@ class AWQQuantizer:
                     try:
                         res = quantize_arena(HostArena.for_tensors(flat), bits=self.bits, group_size=self.group_size,
                                              symmetric=self.symmetric, arith=self.arith, device=dev,
-                                             chunk_bytes=chunk_bytes, packed=False, unpacked=True, sources=flat)
+                                             chunk_bytes=chunk_bytes, packed=False, unpacked=True, sources=flat,
+                                             pin_results=pin)
                         for name in flat:
                             self.logger.info(f"Successfully quantized tensor: {name}")
                         quantized.update(res)
@@ -275,7 +291,8 @@ class AWQQuantizer:
             quantized.update(quantize_arena(arena, bits=self.bits, group_size=self.group_size,
                                             symmetric=self.symmetric, arith=self.arith, device=dev,
                                             chunk_bytes=chunk_bytes, sync=False,
-                                            sources=None if isinstance(tensors, HostArena) else flat))
+                                            sources=None if isinstance(tensors, HostArena) else flat,
+                                            pin_results=isinstance(tensors, HostArena) or pin))
         rest = {}
         for name, tensor in singles.items():           # rows of whole groups: same pipeline, chunked by rows
             if isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu" and \

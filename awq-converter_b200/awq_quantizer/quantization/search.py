@@ -255,14 +255,17 @@ class _PinnedArena:
 
 def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations: Dict[str, torch.Tensor],
                                dev: torch.device, *, pack: bool = False, keep_unpacked: Optional[bool] = None,
-                               wave_bytes: int = 256 << 20) -> Dict[str, Dict[str, torch.Tensor]]:
+                               wave_bytes: int = 256 << 20, pin_results: bool = False) -> Dict[str, Dict[str, torch.Tensor]]:
     """Model-level AWQ from host tensors, streamed: every 2-D tensor that has calibration activations goes
     through the search pipeline (SearchPipeline) and the final K1 pass on W * s_best.
 
     The model is cut into waves of ``wave_bytes``.  An uploader thread stages wave i+1 into pinned memory
     and copies it to the device (copy stream) while wave i is searched and quantized (compute streams) and
-    the results of wave i-1 drain to pinned host arenas (output stream): two device slots, two pinned
-    staging slots, CUDA events between the streams, one host synchronisation at the end.
+    the results of wave i-1 drain to the host (output stream): two device slots, two pinned staging slots,
+    CUDA events between the streams, one host synchronisation at the end.  Results land in a ring of three
+    pinned slots and a drain thread copies them into ordinary tensors (no pinned allocation proportional to
+    the model); with ``pin_results`` they are written straight into per-wave pinned arenas instead (worth
+    it when the pinned blocks are re-used by later models).
 
     Results carry the reference's keys plus ``awq_scale`` / ``alpha`` / ``best_idx`` / ``search_err``
     (+ ``qweight`` / ``qzeros`` with pack).  ``tensor_q`` (4 bytes per element over PCIe) is produced when
@@ -348,6 +351,47 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
     pipe = SearchPipeline(dev, bits=qz.bits, group_size=g, symmetric=qz.symmetric, n_grid=qz.n_grid)
     host_out: Dict[str, Dict[str, torch.Tensor]] = {}
     inflight = []                                       # (device tensors kept alive, D2H-done event)
+
+    # ---- result ring + drain thread (pageable results) ---------------------------------------------
+    def out_bytes(t):
+        C, K = t.shape
+        G = K // g
+        b = _align(C * G * 2) + _align(C * G * 4) + _align(qz.n_grid * 8) + _align(4) + _align(K * 4)
+        if pack:
+            b += _align(C * (-(-K // per)) * 4) + _align(C * (-(-G // per)) * 4)
+        if keep_unpacked:
+            b += _align(C * K * 4)
+        return b
+    n_out_slots = 3
+    ring = []
+    if not pin_results:
+        out_slot_bytes = max(sum(out_bytes(tensors[n]) for n in w) for w in waves)
+        ring = [torch.empty(out_slot_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(min(n_out_slots, len(waves)))]
+    out_q: "queue.Queue" = queue.Queue()
+    slot_free = threading.Semaphore(max(1, len(ring)))
+    drain_err = []
+
+    def drainer():
+        try:
+            torch.cuda.set_device(dev)
+            while True:
+                item = out_q.get()
+                if item is None:
+                    return
+                slot, entries, ev, keep = item
+                ev.synchronize()
+                for name, k, off, nb, dt, shape in entries:
+                    final = torch.empty(shape, dtype=dt)
+                    final.copy_(ring[slot][off:off + nb].view(dt).view(shape))
+                    host_out.setdefault(name, {})[k] = final
+                del keep, item
+                slot_free.release()
+        except BaseException as e:
+            drain_err.append(e)
+            slot_free.release()
+
+    dth = threading.Thread(target=drainer, name="awq-drain", daemon=True)
+    dth.start()
     try:
         for wi, wave in enumerate(waves):
             item = ready.get()
@@ -371,6 +415,25 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
             cd.record(cur)
             compute_done[wi] = cd
             compute_rec[wi].set()
+            if not pin_results:
+                # results -> pinned ring slot on the output stream -> drain thread -> ordinary tensors
+                slot_free.acquire()
+                if drain_err:
+                    raise drain_err[0]
+                slot = wi % len(ring)
+                entries, off = [], 0
+                s_out.wait_event(cd)
+                with torch.cuda.stream(s_out):
+                    for name, o in dev_out.items():
+                        for k, v in o.items():
+                            nb = v.numel() * v.element_size()
+                            ring[slot][off:off + nb].view(v.dtype).view(v.shape).copy_(v, non_blocking=True)
+                            entries.append((name, k, off, nb, v.dtype, tuple(v.shape)))
+                            off += _align(nb)
+                od = torch.cuda.Event()
+                od.record(s_out)
+                out_q.put((slot, entries, od, (dev_out, views)))
+                continue
             # results -> pinned arenas on the output stream
             arena = _PinnedArena()
             for name, o in dev_out.items():
@@ -389,13 +452,19 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
                 inflight.pop(0)
             for (name, k), hv in hviews.items():
                 host_out.setdefault(name, {})[k] = hv
+        out_q.put(None)
+        dth.join()
+        if drain_err:
+            raise drain_err[0]
         s_out.synchronize()
         cur.wait_stream(s_out)
     except BaseException:
         abort.set()
+        out_q.put(None)
         raise
     finally:
         th.join(timeout=60)
+        dth.join(timeout=60)
     out: Dict[str, Dict[str, torch.Tensor]] = {}
     for name in names:
         host = host_out[name]

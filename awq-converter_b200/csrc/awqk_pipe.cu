@@ -5,7 +5,14 @@
 // synchronisation until awqk_pipe_sync().  Replaces the reference's per-tensor
 // tensor.to(device) -> quantize -> .cpu() sequence (main.py:300, 374-380; awq.py:402, 410-412).
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "awqk_common.cuh"
 
@@ -23,6 +30,11 @@ struct awqk_pipe {
   cudaEvent_t ev_in[kBuf] = {}, ev_k[kBuf] = {}, ev_out[kBuf] = {};
   bool used[kBuf] = {};
   size_t elems_max = 0;        // chunk_bytes / 2
+  // gather mode (awqk_pipe_quant_gather): pinned bounce rings, allocated on first use
+  void* h_in[kBuf] = {};
+  uint8_t* h_out[kBuf] = {};
+  size_t h_out_bytes = 0;      // per slot
+  cudaEvent_t ev_h2d[kBuf] = {};
 };
 
 namespace {
@@ -53,6 +65,9 @@ extern "C" void awqk_pipe_destroy(awqk_pipe* p) {
     if (p->ev_in[b]) (void)cudaEventDestroy(p->ev_in[b]);
     if (p->ev_k[b]) (void)cudaEventDestroy(p->ev_k[b]);
     if (p->ev_out[b]) (void)cudaEventDestroy(p->ev_out[b]);
+    if (p->ev_h2d[b]) (void)cudaEventDestroy(p->ev_h2d[b]);
+    if (p->h_in[b]) (void)cudaFreeHost(p->h_in[b]);
+    if (p->h_out[b]) (void)cudaFreeHost(p->h_out[b]);
   }
   if (p->s_in) (void)cudaStreamDestroy(p->s_in);
   if (p->s_k) (void)cudaStreamDestroy(p->s_k);
@@ -206,4 +221,242 @@ extern "C" int awqk_pipe_quant_host(awqk_pipe* p, const void* w_host, int dtype,
     p->used[b] = true;
   }
   return AWQK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Gather mode: the model's tensors stay where the loader put them (ordinary pageable memory).  The
+// tile-aligned arena of quantization/arena.py exists only virtually: tensor i owns the elements
+// [v_i, v_i + numel_i) with v_{i+1} = v_i + roundup(numel_i, 8192).  The calling thread materialises it
+// chunk by chunk in a ring of pinned bounce buffers (parallel memcpy), queues H2D -> K1 -> D2H exactly like
+// the flat mode above, and a drain thread copies every finished chunk from the pinned output ring to the
+// caller's (pageable) result arrays.  Bounded pinned memory (no cudaHostAlloc proportional to the model:
+// pinning runs at ~2.3 GB/s on this box, 20x slower than the pipeline), no second pass over the inputs.
+// Blocking: returns when every result byte is in place.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+int pipe_threads() {
+  static const int n = []() {
+    const char* e = getenv("AWQK_PIPE_THREADS");
+    int v = e ? atoi(e) : 0;
+    if (v <= 0) {
+      const unsigned hc = std::thread::hardware_concurrency();
+      v = hc >= 16 ? 6 : (hc >= 8 ? 4 : 2);
+    }
+    return std::min(v, 16);
+  }();
+  return n;
+}
+
+// memcpy split over a few threads (a single core moves ~10 GB/s; PCIe wants 50)
+void parallel_copy(void* dst, const void* src, size_t bytes, int threads) {
+  if (bytes < ((size_t)2 << 20) || threads <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t per = ((bytes + threads - 1) / threads + 4095) & ~(size_t)4095;
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) {
+    const size_t off = (size_t)t * per;
+    if (off >= bytes) break;
+    const size_t n = std::min(per, bytes - off);
+    pool.emplace_back([=]() { memcpy(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, n); });
+  }
+  memcpy(dst, src, std::min(per, bytes));
+  for (auto& th : pool) th.join();
+}
+
+struct OutLayout {           // byte offsets inside one pinned output slot
+  size_t qp = 0, sc = 0, zp = 0, zq = 0, qu = 0, total = 0;
+};
+
+// page-locked (cudaHostAlloc / cudaHostRegister) host memory?  nullptr counts as "yes" (nothing to copy)
+bool is_pinned(const void* ptr) {
+  if (ptr == nullptr) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* const* src, const int64_t* numel,
+                                      int dtype, int group_size, int bits, int symmetric, int arith,
+                                      int32_t* q_unpacked_host, uint32_t* q_packed_host, void* scales_f16_host,
+                                      int32_t* zp_host, uint32_t* zp_packed_host) {
+  if (p == nullptr || src == nullptr || numel == nullptr || scales_f16_host == nullptr || n_tensors <= 0)
+    return AWQK_E_BADARG;
+  if (bits != 4 && bits != 8) return AWQK_E_BADARG;
+  if (dtype != AWQK_BF16 && dtype != AWQK_FP16 && dtype != AWQK_FP32) return AWQK_E_UNSUPPORTED;
+  if (!(group_size == 32 || group_size == 64 || group_size == 128)) return AWQK_E_UNSUPPORTED;
+  const int per = 32 / bits;
+  const size_t esz = (dtype == AWQK_FP32) ? 4 : 2;
+  constexpr int64_t kTile = 8192;
+  std::vector<int64_t> voff((size_t)n_tensors + 1, 0);
+  for (int i = 0; i < n_tensors; ++i) {
+    if (src[i] == nullptr || numel[i] <= 0 || numel[i] % group_size != 0) return AWQK_E_BADARG;
+    voff[i + 1] = voff[i] + (numel[i] + kTile - 1) / kTile * kTile;
+  }
+  const int64_t n = voff[n_tensors];
+  SetDevice sd(p->device);
+  if (!sd.ok) return AWQK_E_NODEVICE;
+
+  int64_t chunk_elems = (int64_t)(p->chunk_bytes / esz) / kTile * kTile;
+  if ((size_t)chunk_elems > p->elems_max) chunk_elems = (int64_t)p->elems_max / kTile * kTile;
+  if (chunk_elems < kTile) return AWQK_E_WORKSPACE;
+  const size_t E = (size_t)chunk_elems;
+  OutLayout lay;
+  lay.qp = 0;
+  lay.sc = lay.qp + E;                      // packed codes: E * bits / 8 <= E bytes
+  lay.zp = lay.sc + E / 32 * 2;
+  lay.zq = lay.zp + E / 32 * 4;
+  lay.qu = lay.zq + E / 32 * 4;
+  lay.total = lay.qu + (q_unpacked_host ? E * 4 : 0);
+  constexpr int kBuf = awqk_pipe::kBuf;
+  // results that already live in page-locked memory are written by the D2H copies themselves (no bounce, no
+  // drain thread): the caller keeps a cache of pinned result arenas when it converts model after model
+  const bool direct = is_pinned(q_unpacked_host) && is_pinned(q_packed_host) && is_pinned(scales_f16_host) &&
+                      is_pinned(zp_host) && is_pinned(zp_packed_host);
+  for (int b = 0; b < kBuf; ++b) {
+    if (p->h_in[b] == nullptr) AWQK_CUDA(cudaHostAlloc(&p->h_in[b], p->chunk_bytes, cudaHostAllocDefault));
+    if (p->ev_h2d[b] == nullptr) AWQK_CUDA(cudaEventCreateWithFlags(&p->ev_h2d[b], cudaEventDisableTiming));
+    if (q_unpacked_host != nullptr && p->d_qu[b] == nullptr)
+      AWQK_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_qu[b]), p->elems_max * 4));
+  }
+  if (!direct && p->h_out_bytes < lay.total) {
+    for (int b = 0; b < kBuf; ++b) {
+      if (p->h_out[b]) { AWQK_CUDA(cudaStreamSynchronize(p->s_out)); (void)cudaFreeHost(p->h_out[b]); p->h_out[b] = nullptr; }
+      AWQK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p->h_out[b]), lay.total, cudaHostAllocDefault));
+    }
+    p->h_out_bytes = lay.total;
+  }
+  // everything queued earlier on this pipe must have left the device slots before they are rewired
+  AWQK_CUDA(cudaStreamSynchronize(p->s_out));
+
+  const int threads = pipe_threads();
+  const int64_t n_chunks = (n + chunk_elems - 1) / chunk_elems;
+  // ---- drain thread: chunk c is copied out once its D2H event fired; then its output slot is free ----
+  std::mutex mu;
+  std::condition_variable cv;
+  int64_t queued = 0, drained = 0;          // chunks whose GPU work is enqueued / whose results are in place
+  int status = AWQK_OK;
+  bool stop = false;
+  const int device = p->device;
+  std::thread drainer([&]() {
+    (void)cudaSetDevice(device);
+    for (int64_t c = 0; c < n_chunks && !direct; ++c) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return queued > c || stop; });
+        if (queued <= c) return;            // stopped before this chunk was queued
+      }
+      const int b = (int)(c % kBuf);
+      if (cudaEventSynchronize(p->ev_out[b]) != cudaSuccess) {
+        std::lock_guard<std::mutex> lk(mu);
+        status = AWQK_E_CUDA;
+        drained = c + 1;
+        cv.notify_all();
+        continue;
+      }
+      const int64_t e0 = c * chunk_elems, ne = std::min<int64_t>(chunk_elems, n - e0), ng = ne / group_size;
+      const uint8_t* o = p->h_out[b];
+      if (q_packed_host) parallel_copy(q_packed_host + e0 / per, o + lay.qp, (size_t)(ne / per) * 4, threads);
+      if (q_unpacked_host) parallel_copy(q_unpacked_host + e0, o + lay.qu, (size_t)ne * 4, threads);
+      memcpy(static_cast<uint16_t*>(scales_f16_host) + e0 / group_size, o + lay.sc, (size_t)ng * 2);
+      if (zp_host) memcpy(zp_host + e0 / group_size, o + lay.zp, (size_t)ng * 4);
+      if (zp_packed_host) memcpy(zp_packed_host + e0 / group_size / per, o + lay.zq, (size_t)((ng + per - 1) / per) * 4);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        drained = c + 1;
+      }
+      cv.notify_all();
+    }
+  });
+  auto finish = [&](int rc) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    drainer.join();
+    return rc != AWQK_OK ? rc : status;
+  };
+#define AWQK_CUDA_G(expr)                                                \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) {                                             \
+      ::awqk::set_cuda_error(_e, #expr, __FILE__, __LINE__);             \
+      return finish(AWQK_E_CUDA);                                        \
+    }                                                                    \
+  } while (0)
+
+  int ti = 0;                               // first tensor that may overlap the current chunk
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int b = (int)(c % kBuf);
+    const int64_t e0 = c * chunk_elems, ne = std::min<int64_t>(chunk_elems, n - e0), e1 = e0 + ne;
+    const int64_t ng = ne / group_size;
+    if (c >= kBuf) {
+      AWQK_CUDA_G(cudaEventSynchronize(p->ev_h2d[b]));          // pinned input slot: its H2D has finished
+      if (!direct) {
+        std::unique_lock<std::mutex> lk(mu);                     // pinned output slot: chunk c - kBuf is drained
+        cv.wait(lk, [&]() { return drained >= c - kBuf + 1; });
+      }
+      AWQK_CUDA_G(cudaStreamWaitEvent(p->s_in, p->ev_k[b], 0)); // device input slot: K1 of chunk c - kBuf has read it
+    }
+    // ---- stage: gather the pieces of the virtual arena that fall into [e0, e1) ----
+    uint8_t* hin = static_cast<uint8_t*>(p->h_in[b]);
+    while (ti < n_tensors && voff[ti + 1] <= e0) ++ti;
+    for (int i = ti; i < n_tensors && voff[i] < e1; ++i) {
+      const int64_t t0 = std::max<int64_t>(voff[i], e0), t1 = std::min<int64_t>(voff[i] + numel[i], e1);
+      if (t1 > t0)
+        parallel_copy(hin + (size_t)(t0 - e0) * esz, static_cast<const uint8_t*>(src[i]) + (size_t)(t0 - voff[i]) * esz,
+                      (size_t)(t1 - t0) * esz, threads);
+      const int64_t z0 = std::max<int64_t>(voff[i] + numel[i], e0), z1 = std::min<int64_t>(voff[i + 1], e1);
+      if (z1 > z0) memset(hin + (size_t)(z0 - e0) * esz, 0, (size_t)(z1 - z0) * esz);     // tile padding
+    }
+    // ---- queue H2D -> K1 -> D2H (into the pinned output slot) ----
+    AWQK_CUDA_G(cudaMemcpyAsync(p->d_in[b], hin, (size_t)ne * esz, cudaMemcpyHostToDevice, p->s_in));
+    AWQK_CUDA_G(cudaEventRecord(p->ev_h2d[b], p->s_in));
+    AWQK_CUDA_G(cudaStreamWaitEvent(p->s_k, p->ev_h2d[b], 0));
+    if (c >= kBuf) AWQK_CUDA_G(cudaStreamWaitEvent(p->s_k, p->ev_out[b], 0));   // device output slot drained to the host
+    const int rc = awqk_group_quant(p->d_in[b], dtype, 1, ne, group_size, bits, symmetric, arith,
+                                    q_unpacked_host ? p->d_qu[b] : nullptr, q_packed_host ? p->d_qp[b] : nullptr,
+                                    p->d_sc[b], zp_host ? p->d_zp[b] : nullptr, zp_packed_host ? p->d_zpp[b] : nullptr,
+                                    nullptr, p->s_k);
+    if (rc != AWQK_OK) return finish(rc);
+    AWQK_CUDA_G(cudaEventRecord(p->ev_k[b], p->s_k));
+    AWQK_CUDA_G(cudaStreamWaitEvent(p->s_out, p->ev_k[b], 0));
+    uint8_t* o = p->h_out[b];
+    void* dst_qp = direct ? static_cast<void*>(q_packed_host + e0 / per) : o + lay.qp;
+    void* dst_qu = direct ? static_cast<void*>(q_unpacked_host + e0) : o + lay.qu;
+    void* dst_sc = direct ? static_cast<void*>(static_cast<uint16_t*>(scales_f16_host) + e0 / group_size) : o + lay.sc;
+    void* dst_zp = direct ? static_cast<void*>(zp_host + e0 / group_size) : o + lay.zp;
+    void* dst_zq = direct ? static_cast<void*>(zp_packed_host + e0 / group_size / per) : o + lay.zq;
+    if (q_packed_host)
+      AWQK_CUDA_G(cudaMemcpyAsync(dst_qp, p->d_qp[b], (size_t)(ne / per) * 4, cudaMemcpyDeviceToHost, p->s_out));
+    if (q_unpacked_host)
+      AWQK_CUDA_G(cudaMemcpyAsync(dst_qu, p->d_qu[b], (size_t)ne * 4, cudaMemcpyDeviceToHost, p->s_out));
+    AWQK_CUDA_G(cudaMemcpyAsync(dst_sc, p->d_sc[b], (size_t)ng * 2, cudaMemcpyDeviceToHost, p->s_out));
+    if (zp_host) AWQK_CUDA_G(cudaMemcpyAsync(dst_zp, p->d_zp[b], (size_t)ng * 4, cudaMemcpyDeviceToHost, p->s_out));
+    if (zp_packed_host)
+      AWQK_CUDA_G(cudaMemcpyAsync(dst_zq, p->d_zpp[b], (size_t)((ng + per - 1) / per) * 4, cudaMemcpyDeviceToHost, p->s_out));
+    AWQK_CUDA_G(cudaEventRecord(p->ev_out[b], p->s_out));
+    p->used[b] = true;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      queued = c + 1;
+    }
+    cv.notify_all();
+  }
+  if (direct) AWQK_CUDA_G(cudaStreamSynchronize(p->s_out));
+#undef AWQK_CUDA_G
+  if (!direct) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&]() { return drained >= n_chunks; });
+  }
+  drainer.join();
+  return status;
 }

@@ -156,6 +156,18 @@ AWQK_API int awqk_pipe_quant_host(awqk_pipe* p, const void* w_host, int dtype, i
                          int group_size, int bits, int symmetric, int arith,
                          int32_t* q_unpacked_host, uint32_t* q_packed_host, void* scales_f16_host,
                          int32_t* zp_host, uint32_t* zp_packed_host);
+/* Gather mode: the same pipeline over a VIRTUAL arena of n_tensors host tensors (ordinary pageable memory is
+ * fine): tensor i owns elements [v_i, v_i + numel[i]) with v_0 = 0, v_{i+1} = v_i + roundup(numel[i], 8192).
+ * The pipe stages it chunk by chunk through its own bounded ring of pinned buffers (AWQK_PIPE_THREADS memcpy
+ * threads, default by core count) and a drain thread copies finished chunks into the result arrays, which are
+ * flat over the virtual arena exactly as in awqk_pipe_quant_host (C = 1, K = v_n).  Every numel[i] must be a
+ * multiple of group_size (of group_size * 32 / bits when zp_packed_host is given, so that packed zero words
+ * never straddle tensors).  BLOCKING: returns when all results are in place.  Replaces the reference's
+ * per-tensor tensor.to(device) / .cpu() round trips (main.py:300, 374-380) for a whole model. */
+AWQK_API int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* const* src, const int64_t* numel,
+                           int dtype, int group_size, int bits, int symmetric, int arith,
+                           int32_t* q_unpacked_host, uint32_t* q_packed_host, void* scales_f16_host,
+                           int32_t* zp_host, uint32_t* zp_packed_host);
 /* wait for everything queued on the pipe */
 AWQK_API int awqk_pipe_sync(awqk_pipe* p);
 

@@ -476,26 +476,48 @@ def test_default_quantize_model_is_pipelined_and_reference_exact(native_lib, cud
             assert_quant_equal(out[n], loop[n], n + "/loop")
 
 
-@pytest.mark.parametrize("segment_bytes", [1 << 14, 48 << 10, 1 << 20])
-def test_arena_staged_from_pageable_tensors(native_lib, cuda_device, segment_bytes):
-    """quantize_arena(sources=...): the arena is filled segment by segment while the pipeline already runs on
-    the previous segment -- segment ends inside tensors, at tensor ends and across tile padding"""
+@pytest.mark.parametrize("chunk_bytes", [1 << 16, 3 << 16, 32 << 20])
+@pytest.mark.parametrize("layout", ["packed", "reference", "both"])
+def test_gather_pipeline_from_pageable_tensors(native_lib, cuda_device, chunk_bytes, layout):
+    """awqk_pipe_quant_gather: virtual arena over pageable tensors, pinned bounce rings inside the pipe, results
+    drained into pageable arrays -- chunks ending inside tensors, at tensor ends and inside tile padding; many
+    more chunks than ring slots"""
     from awq_quantizer.quantization.arena import HostArena, quantize_arena
-    shapes = {"a": (24, 1024), "b": (1024,), "c": (40, 2048), "d": (8, 3, 1024), "e": (3, 1024), "h": (16, 1024)}
-    tensors = {n: datagen.weights(s, "fp16" if n == "h" else "bf16", datagen.seed_of("stage", n)) for n, s in shapes.items()}
+    shapes = {"a": (24, 1024), "b": (1024,), "c": (200, 2048), "d": (8, 3, 1024), "e": (3, 1024), "h": (16, 1024),
+              "f": (1, 9 * 8192 + 1024)}
+    tensors = {n: datagen.weights(s, "fp16" if n == "h" else "bf16", datagen.seed_of("gather", n)) for n, s in shapes.items()}
     arena = HostArena.for_tensors(tensors)
-    for dt, buf in arena.buffers.items():           # poison the slots: stale data must never reach the GPU
-        buf.view(torch.int16)[:] = 0x7FC1
-    for name, off, n in [x for lay in arena.layout.values() for x in lay]:
-        dt = arena.specs[name][1]
-        arena.buffers[dt][off + n:off + (n + 8191) // 8192 * 8192].zero_()
-    res = quantize_arena(arena, bits=4, group_size=128, symmetric=False, arith="native", device=cuda_device,
-                         chunk_bytes=1 << 16, packed=True, unpacked=True, want_zero_points=True, sources=tensors,
-                         segment_bytes=segment_bytes)
-    for n, t in tensors.items():
-        want = O.pack_result(O.group_quant_vec(t, 4, 128, False, True))
-        assert_quant_equal(res[n], want, n, keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
-        assert torch.equal(arena.views[n], t)
+    assert not arena.buffers                                   # layout only: nothing was pinned
+    packed, unpacked = layout in ("packed", "both"), layout in ("reference", "both")
+    for rep in range(2):                                       # second call reuses the rings
+        res = quantize_arena(arena, bits=4, group_size=128, symmetric=bool(rep), arith="native", device=cuda_device,
+                             chunk_bytes=chunk_bytes, packed=packed, unpacked=unpacked, want_zero_points=True,
+                             sources=tensors, pin_results=bool(rep))      # rep 1: direct D2H into pinned results
+        for n, t in tensors.items():
+            want = O.pack_result(O.group_quant_vec(t, 4, 128, bool(rep), True))
+            keys = ("scales", "zero_points") + (("qweight", "qzeros") if packed else ()) + (("tensor_q",) if unpacked else ())
+            assert_quant_equal(res[n], want, f"{n}/{rep}", keys=keys)
+            assert res[n]["scales"].is_pinned() == bool(rep)
+
+
+def test_gather_c_abi_errors(native_lib, cuda_device):
+    import ctypes as C
+    from awq_quantizer import _native as N
+    w = datagen.weights((4, 1000), "bf16", 1)                   # 4000 elements: not a multiple of the group size
+    sc = torch.empty(64, dtype=torch.float16)
+    h = C.c_void_p()
+    assert native_lib.awqk_pipe_create(0, 1 << 16, C.byref(h)) == 0
+    try:
+        ptrs = (C.c_void_p * 1)(w.data_ptr())
+        nums = (C.c_int64 * 1)(4000)
+        args = (N.BF16, 128, 4, 0, N.ARITH_NATIVE, None, None, sc.data_ptr(), None, None)
+        assert native_lib.awqk_pipe_quant_gather(h, 1, ptrs, nums, *args) == -1
+        nums[0] = 0
+        assert native_lib.awqk_pipe_quant_gather(h, 1, ptrs, nums, *args) == -1
+        assert native_lib.awqk_pipe_quant_gather(h, 0, ptrs, nums, *args) == -1
+        assert native_lib.awqk_pipe_quant_gather(None, 1, ptrs, nums, *args) == -1
+    finally:
+        native_lib.awqk_pipe_destroy(h)
 
 
 @pytest.mark.parametrize("dt", ["bf16", "fp16"])

@@ -246,11 +246,11 @@ def test_streamed_model_search_many_waves(native_lib, cuda_device):
         tensors[f"t{i}"] = w
         acts[f"t{i}"] = X[s[1]]
     qz = AWQQuantizer(bits=4, group_size=128, symmetric=False, device="cuda:0", logger_level="ERROR", n_grid=6)
-    for wave_bytes in (1, 70_000, 1 << 30):
-        out = quantize_model_with_search(qz, tensors, acts, cuda_device, pack=True, wave_bytes=wave_bytes)
+    for wave_bytes, pin in ((1, False), (70_000, False), (70_000, True), (1 << 30, False)):
+        out = quantize_model_with_search(qz, tensors, acts, cuda_device, pack=True, wave_bytes=wave_bytes, pin_results=pin)
         assert list(out) == list(tensors)
         for n, w in tensors.items():
             single = qz.quantize(w.cpu(), activations=acts[n], pack=True)
             assert int(out[n]["best_idx"]) == int(single["best_idx"]), (n, wave_bytes)
             assert_quant_equal(out[n], single, f"{n}/{wave_bytes}", keys=("scales", "zero_points", "qweight", "qzeros"))
-            assert out[n]["qweight"].device.type == "cpu" and out[n]["qweight"].is_pinned()
+            assert out[n]["qweight"].device.type == "cpu" and out[n]["qweight"].is_pinned() == pin
