@@ -41,6 +41,7 @@ SIGNATURES = {
                                     _vp, _vp]),
     "awqk_pipe_quant_gather": (_int, [_vp, _int, C.POINTER(_vp), C.POINTER(_i64), _int, _int, _int, _int, _int,
                                       _vp, _vp, _vp, _vp, _vp]),
+    "awqk_host_copy": (_int, [_vp, _vp, C.c_size_t, _int]),
     "awqk_pipe_sync": (_int, [_vp]),
 }
 
@@ -93,3 +94,12 @@ def ptr(t) -> int:
 def stream_ptr(device) -> int:
     import torch
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def host_copy(dst, src) -> None:
+    """dst.copy_(src) for contiguous CPU tensors of equal dtype / size through the native multi-threaded memcpy
+    (torch's copy_ is single-threaded under torchrun's OMP_NUM_THREADS=1 and holds no more than one core)"""
+    if dst.dtype != src.dtype or dst.numel() != src.numel() or not dst.is_contiguous() or not src.is_contiguous():
+        dst.copy_(src)
+        return
+    check(lib().awqk_host_copy(dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), 0), "awqk_host_copy")

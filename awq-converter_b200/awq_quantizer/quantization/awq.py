@@ -64,6 +64,7 @@ class AWQQuantizer:
         # pipeline), so it only pays when the allocation is re-used.  None = adaptive: the first model of this
         # quantizer gets ordinary (pageable) results drained through the pipeline's bounded pinned ring, later
         # models get pinned results straight from the D2H copies (torch's pinned allocator caches the blocks).
+        # Searched tensors always go through the ring unless this is True (their drain hides under the search).
         self.pin_results = pin_results
         self._models_done = 0
         # awq.py:70-73: default device is CUDA.  (No silent CPU downgrade here.)
@@ -232,7 +233,7 @@ class AWQQuantizer:
             try:
                 searched = quantize_model_with_search(self, {n: t for n, t in tensors.items() if n in activations},
                                                       activations, dev, pack=pack, keep_unpacked=keep_unpacked,
-                                                      pin_results=pin)
+                                                      pin_results=bool(self.pin_results))
             except Exception as e:
                 self.logger.error(f"Activation-aware search failed: {e}")
             rest = {n: t for n, t in tensors.items() if n not in searched}

@@ -331,7 +331,7 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
                     src = t.detach()
                     if not src.is_pinned():
                         hv = h_slot[slot][off:off + nb].view(t.dtype).view(t.shape)
-                        hv.copy_(src)
+                        N.host_copy(hv, src)
                         src = hv
                     with torch.cuda.stream(s_copy):
                         dv.copy_(src, non_blocking=True)
@@ -382,7 +382,7 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
                 ev.synchronize()
                 for name, k, off, nb, dt, shape in entries:
                     final = torch.empty(shape, dtype=dt)
-                    final.copy_(ring[slot][off:off + nb].view(dt).view(shape))
+                    N.host_copy(final, ring[slot][off:off + nb].view(dt).view(shape))
                     host_out.setdefault(name, {})[k] = final
                 del keep, item
                 slot_free.release()

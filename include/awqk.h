@@ -168,6 +168,10 @@ AWQK_API int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* con
                            int dtype, int group_size, int bits, int symmetric, int arith,
                            int32_t* q_unpacked_host, uint32_t* q_packed_host, void* scales_f16_host,
                            int32_t* zp_host, uint32_t* zp_packed_host);
+/* memcpy split over `threads` host threads (0 = the pipe's default: AWQK_PIPE_THREADS or by core count).  One
+ * core moves ~10 GB/s, a PCIe 5 x16 link wants 50: the staging copies between pageable tensors and the pinned
+ * rings of the Python-side streams (quantization/search.py) go through this. */
+AWQK_API int awqk_host_copy(void* dst, const void* src, size_t bytes, int threads);
 /* wait for everything queued on the pipe */
 AWQK_API int awqk_pipe_sync(awqk_pipe* p);
 

@@ -68,3 +68,18 @@ def test_argument_validation_without_gpu(native_lib):
     assert L.awqk_bf16_to_fp16(None, None, 0, None) == 0
     assert L.awqk_bf16_to_fp16(None, None, -1, None) == -1
     assert L.awqk_dequant(None, None, None, 1, 1, 1, None, None) == -1
+
+
+def test_host_copy_without_gpu(native_lib):
+    """awqk_host_copy is plain host code (parallel memcpy): usable, and exact, without a device"""
+    import torch
+    from awq_quantizer import _native
+    a = torch.arange(3 * (1 << 20) + 17, dtype=torch.int32)
+    b = torch.zeros_like(a)
+    _native.host_copy(b, a)
+    assert torch.equal(a, b)
+    c = torch.arange(600, dtype=torch.float32).reshape(200, 3)[:, :2]     # non-contiguous -> torch path
+    d = torch.empty(200, 2)
+    _native.host_copy(d, c)
+    assert torch.equal(c, d)
+    assert native_lib.awqk_host_copy(None, None, 16, 2) == -1

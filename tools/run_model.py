@@ -25,6 +25,7 @@ ap.add_argument("--n-grid", type=int, default=20)
 ap.add_argument("--no-search", action="store_true")
 ap.add_argument("--from-host", choices=["pageable", "pinned"], default=None,
                 help="end to end through the public API: weights start in host memory, packed results end there")
+ap.add_argument("--pin-results", choices=["auto", "0", "1"], default="auto")
 args = ap.parse_args()
 
 rank, world = parallel.init_distributed()
@@ -60,7 +61,8 @@ if args.from_host:
     acts = {} if args.no_search else {n: host_x[s[1]] for n, s, ck in shard if ck is not None}
     del xs
     torch.cuda.empty_cache()
-    qz = AWQQuantizer(bits=4, group_size=g, symmetric=False, device=f"cuda:{local}", logger_level="ERROR", n_grid=args.n_grid)
+    qz = AWQQuantizer(bits=4, group_size=g, symmetric=False, device=f"cuda:{local}", logger_level="ERROR", n_grid=args.n_grid,
+                      pin_results=None if args.pin_results == "auto" else args.pin_results == "1")
     times = []
     for it in range(4):
         if world > 1:
