@@ -156,6 +156,17 @@ def partition_tensors(tensors: Dict[str, torch.Tensor], num_partitions: int) -> 
     return [{n: tensors[n] for n in b} for b in bins]
 
 
+def _own_storage(qd: dict) -> dict:
+    """torch.save pickles the WHOLE storage behind a view; the pipeline returns views of model-sized result
+    arrays, so every tensor is detached into its own storage first (one host copy of the results)"""
+    out = {}
+    for k, v in qd.items():
+        if isinstance(v, torch.Tensor) and v.numel() * v.element_size() != v.untyped_storage().nbytes():
+            v = v.clone()
+        out[k] = v
+    return out
+
+
 def _flatten_for_safetensors(chunk: Dict[str, dict]) -> Dict[str, torch.Tensor]:
     rename = {"tensor_q": "q"}
     flat = {}
@@ -186,7 +197,7 @@ def save_model_in_chunks(tensors: Dict[str, dict], output_dir: str, chunk_size: 
             save_file(_flatten_for_safetensors(part), base + ".safetensors")
             files.append(os.path.basename(base) + ".safetensors")
         else:
-            torch.save(part, base + ".pt")
+            torch.save({n: _own_storage(qd) for n, qd in part.items()}, base + ".pt")
             files.append(os.path.basename(base) + ".pt")
         if logger:
             logger.info(f"Saved chunk {c + 1}/{num_chunks} with {len(part)} tensors")
@@ -277,15 +288,16 @@ def main(argv=None) -> int:
                 done.update(qz.quantize_model(searched, activations={n: calib[n] for n in searched}, pack=args.pack,
                                               keep_unpacked=True))
                 shard = {n: t for n, t in shard.items() if n not in done}
-            batches = prepare_tensors_for_quantization(shard, device, args.max_memory, args.batch_size, logger)
-            with ThreadPoolExecutor(max_workers=max(1, args.num_workers)) as ex:
-                futs = [ex.submit(quantize_tensor_batch, list(b.items()), qz, device, logger, args.pack) for b in batches]
-                for i, fut in enumerate(futs):
-                    try:
-                        done.update(fut.result())
-                        logger.info(f"Completed batch {i + 1}/{len(batches)} on {device}")
-                    except Exception as e:
-                        logger.error(f"Error processing batch {i} on {device}: {e}")
+            # the whole shard in ONE call: every whole-group tensor streams through the native gather pipeline
+            # (bounded pinned rings, no per-tensor upload / kernel / download round trip as in main.py:333-392);
+            # what it cannot take (ragged rows, tiny tensors ...) falls back to per-tensor calls inside.
+            # --batch_size / --num_workers / --prefetch_factor are accepted for compatibility and not needed.
+            for name in shard:
+                logger.info(f"Quantizing tensor: {name} on {device}")
+            try:
+                done.update(qz.quantize_model(shard, pack=args.pack, keep_unpacked=True))
+            except Exception as e:
+                logger.error(f"Error processing shard on {device}: {e}")
             return done
 
         quantized: Dict[str, dict] = {}

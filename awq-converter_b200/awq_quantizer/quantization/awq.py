@@ -222,8 +222,8 @@ class AWQQuantizer:
 
         ``activations`` (name -> calibration activations [tokens, in_features]) turns on the activation-aware
         alpha search for those tensors (quantization/search.py: streamed upload / search / download); all
-        other tensors take the paths above.  With ``pack`` the searched results carry ``tensor_q`` only if
-        ``keep_unpacked`` is true (4 bytes per element over PCIe), like the packed path."""
+        other tensors take the paths above.  With ``pack`` the results carry ``tensor_q`` / ``zero_points`` only
+        if ``keep_unpacked`` is true (4 more bytes per element over PCIe)."""
         pin = self._pin_now() if _pin is None else _pin          # one decision per model
         if activations:
             from .search import quantize_model_with_search
@@ -275,6 +275,7 @@ class AWQQuantizer:
         dev = self._cuda_device()
         self._check_zero_point_mode()
         quantized = {}
+        keep = bool(keep_unpacked)                     # also return the reference's tensor_q / zero_points
         if isinstance(tensors, HostArena):
             arena, singles = tensors, {}
             bad = [n for n, (shp, dt) in arena.specs.items() if not arena_eligible(shp, dt, self.group_size, self.bits)]
@@ -283,7 +284,8 @@ class AWQQuantizer:
         else:
             flat, singles = {}, {}
             for name, t in tensors.items():
-                if isinstance(t, torch.Tensor) and arena_eligible(tuple(t.shape), t.dtype, self.group_size, self.bits):
+                if isinstance(t, torch.Tensor) and t.device.type == "cpu" and \
+                        arena_eligible(tuple(t.shape), t.dtype, self.group_size, self.bits):
                     flat[name] = t
                 else:
                     singles[name] = t
@@ -291,12 +293,12 @@ class AWQQuantizer:
         if arena is not None:
             quantized.update(quantize_arena(arena, bits=self.bits, group_size=self.group_size,
                                             symmetric=self.symmetric, arith=self.arith, device=dev,
-                                            chunk_bytes=chunk_bytes, sync=False,
+                                            chunk_bytes=chunk_bytes, sync=False, unpacked=keep, want_zero_points=keep,
                                             sources=None if isinstance(tensors, HostArena) else flat,
                                             pin_results=isinstance(tensors, HostArena) or pin))
         rest = {}
         for name, tensor in singles.items():           # rows of whole groups: same pipeline, chunked by rows
-            if isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu" and \
+            if not keep and isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu" and \
                     pipe_eligible(tuple(tensor.shape), tensor.dtype, self.group_size, self.bits):
                 r = quantize_rows_pipelined(tensor, bits=self.bits, group_size=self.group_size, symmetric=self.symmetric,
                                             arith=self.arith, device=dev, chunk_bytes=chunk_bytes, sync=False)
@@ -308,7 +310,7 @@ class AWQQuantizer:
             r.pop("_keepalive", None)
         for name, tensor in rest.items():              # ragged rows, odd group sizes, fp64, numel < group_size ...
             try:
-                quantized[name] = self.quantize(tensor, pack=True, keep_unpacked=False)
+                quantized[name] = self.quantize(tensor, pack=True, keep_unpacked=keep)
             except Exception as e:
                 self.logger.error(f"Error quantizing tensor: {name}, error: {e}")
         return quantized

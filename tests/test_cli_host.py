@@ -88,6 +88,14 @@ def test_save_chunks_pt_and_safetensors(tmp_path):
         assert f"t1.{suffix}" in flat
     assert flat["t1.q"].dtype == torch.int32 and flat["t1.scales"].dtype == torch.float16
     assert "t0.qweight" in flat and "t1.qweight" not in flat
+    # results that are views of one model-sized array (the pipeline's layout) must not drag it into every chunk
+    big = torch.arange(1 << 20, dtype=torch.int32)
+    v = {f"v{i}": dict(fake_qdict((4, 256)), tensor_q=big[i * 1024:(i + 1) * 1024].view(4, 256)) for i in range(4)}
+    cli.save_model_in_chunks(v, str(tmp_path / "views"), chunk_size=1)
+    import os
+    assert all(os.path.getsize(tmp_path / "views" / f"model_chunk_{i:04d}.pt") < 64 << 10 for i in range(4))
+    back = torch.load(tmp_path / "views" / "model_chunk_0002.pt")
+    assert torch.equal(back["v2"]["tensor_q"], v["v2"]["tensor_q"])
 
 
 def test_loader_contract_and_arena(tmp_path):
