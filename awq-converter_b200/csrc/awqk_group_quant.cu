@@ -449,7 +449,7 @@ static int launch_generic(const InT* w, int64_t C, int64_t K, int g, int64_t G, 
 }
 
 // awqk_group_quant_tma.cu
-int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, bool sym, int arith,
+int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, int bits, bool sym, int arith,
                            uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                            int zq_log2, cudaStream_t st);
 
@@ -502,12 +502,13 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
   QuantOut out{q_unpacked, q_packed, reinterpret_cast<__half*>(scales_f16), zp, zp_packed};
 
   if (path == 1) {
-    const bool tma_plain = bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) &&
+    const bool tma_plain = (dtype == AWQK_BF16 || dtype == AWQK_FP16) &&
                            (q_packed != nullptr || q_unpacked != nullptr) && col_scale == nullptr && tma_path_enabled() &&
                            (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0;
-    // rows of 1 / 2 / 4 groups: K1 v2 writes one zero-padded word per row itself
-    const int zq_log2 = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : 3;
-    const bool flat_zp = (G % per) == 0 || (tma_plain && zq_log2 < 3);
+    // rows of 1 / 2 / 4 groups (fewer than a packed word): K1 v2 writes one zero-padded word per row itself
+    const int full_log2 = (bits == 4) ? 3 : 2;                 // log2(zero points per word)
+    const int zq_log2 = (G % per == 0) ? full_log2 : (G == 1) ? 0 : (G == 2) ? 1 : (G == 4 && bits == 4) ? 2 : full_log2;
+    const bool flat_zp = (G % per) == 0 || (tma_plain && zq_log2 < full_log2);
     int32_t* zp_for_pack = zp;
     if (zp_packed != nullptr && !flat_zp) {
       if (zp == nullptr) return AWQK_E_WORKSPACE;  // row-wise zero packing needs the int32 zeros
@@ -517,7 +518,7 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
     int rc;
     if (tma_plain) {
       // K1 v2: TMA-staged, packed-math kernel (int4 pack path and the reference's int32 code layout)
-      rc = launch_group_quant_tma(w, dtype, n, group_size, sym, arith, q_packed, q_unpacked, scales_f16, zp,
+      rc = launch_group_quant_tma(w, dtype, n, group_size, bits, sym, arith, q_packed, q_unpacked, scales_f16, zp,
                                   out.zp_packed, zq_log2, st);
     } else if (bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) && (q_packed != nullptr || q_unpacked != nullptr) &&
                col_scale != nullptr && tma_path_enabled() && (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0 &&

@@ -109,11 +109,11 @@ __device__ __forceinline__ float v2_fmax_nan(float a, float b) {
 
 // pair of clamped unsigned codes (lo | hi << 16), each in [0, 2^BITS - 1], from a packed pair of
 // exact quotients q = x / s.  A selects the reference's arithmetic dtype.
-template <int A, int QMIN>
+template <int A, int QMIN, int BITS>
 struct PairQuant;
 
-template <int QMIN>
-struct PairQuant<AR_F32, QMIN> {
+template <int QMIN, int BITS>
+struct PairQuant<AR_F32, QMIN, BITS> {
   // v = q + zp (fp32), t = v + 1.5*2^23 -> low 16 bits of each t hold round(v) as an s16
   // (|v| < 2^14 guaranteed by the fast-group predicate)
   // the magic constant carries -QMIN, so the low half IS the unsigned code before clamping
@@ -124,11 +124,11 @@ struct PairQuant<AR_F32, QMIN> {
   __device__ __forceinline__ uint32_t run(float2 q) const {
     const float2 t = __fadd2_rn(__fadd2_rn(q, zp2), magic2);
     const uint32_t both = __byte_perm(__float_as_uint(t.x), __float_as_uint(t.y), 0x5410);
-    return __vimin_s16x2_relu(both, 0x000F000Fu);
+    return __vimin_s16x2_relu(both, (uint32_t)((1 << BITS) - 1) * 0x00010001u);
   }
 };
 template <int QMIN>
-struct PairQuant<AR_BF16, QMIN> {
+struct PairQuant<AR_BF16, QMIN, 4> {
   // a = bf16(q); b = bf16(a + zp); t = bf16(b + 192): [128,256) has ulp 1 -> bits = 0x4340 + round(b)
   __nv_bfloat162 zp2, magic2;
   uint32_t rebase;
@@ -145,7 +145,7 @@ struct PairQuant<AR_BF16, QMIN> {
   }
 };
 template <int QMIN>
-struct PairQuant<AR_F16, QMIN> {
+struct PairQuant<AR_F16, QMIN, 4> {
   // fp16: [1024,2048) has ulp 1 -> magic 1536 = 0x6600
   __half2 zp2, magic2;
   uint32_t rebase;
@@ -159,6 +159,37 @@ struct PairQuant<AR_F16, QMIN> {
     const __half2 a = __float22half2_rn(q);
     const __half2 t = __hadd2(__hadd2(a, zp2), magic2);
     return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), rebase, 0x000F000Fu);
+  }
+};
+
+// 8 bit in the reference's bf16 / fp16 arithmetic: a = A(q), b = A(a + zp) as above, but codes up to 255 leave
+// the window in which a bf16 / fp16 magic constant has ulp 1 -- b is widened to fp32 (exact) and rounded with the
+// fp32 magic instead (rint of an A-representable value is the same number in either format).
+template <int QMIN>
+struct PairQuant<AR_BF16, QMIN, 8> {
+  __nv_bfloat162 zp2;
+  float2 magic2;
+  __device__ __forceinline__ void prepare() { magic2 = make_float2(12582912.0f - (float)QMIN, 12582912.0f - (float)QMIN); }
+  __device__ __forceinline__ void init(float zp) { zp2 = __float2bfloat162_rn(zp); }
+  __device__ __forceinline__ uint32_t run(float2 q) const {
+    const __nv_bfloat162 b = __hadd2(__float22bfloat162_rn(q), zp2);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&b);
+    const float2 t = __fadd2_rn(make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u)), magic2);
+    const uint32_t both = __byte_perm(__float_as_uint(t.x), __float_as_uint(t.y), 0x5410);
+    return __vimin_s16x2_relu(both, 0x00FF00FFu);
+  }
+};
+template <int QMIN>
+struct PairQuant<AR_F16, QMIN, 8> {
+  __half2 zp2;
+  float2 magic2;
+  __device__ __forceinline__ void prepare() { magic2 = make_float2(12582912.0f - (float)QMIN, 12582912.0f - (float)QMIN); }
+  __device__ __forceinline__ void init(float zp) { zp2 = __float2half2_rn(zp); }
+  __device__ __forceinline__ uint32_t run(float2 q) const {
+    const __half2 b = __hadd2(__float22half2_rn(q), zp2);
+    const float2 t = __fadd2_rn(__half22float2(b), magic2);
+    const uint32_t both = __byte_perm(__float_as_uint(t.x), __float_as_uint(t.y), 0x5410);
+    return __vimin_s16x2_relu(both, 0x00FF00FFu);
   }
 };
 
@@ -203,14 +234,17 @@ __device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
   return r;
 }
 
-template <typename InT, int A, int G, bool SYM, bool UNPACKED, bool CS>
+template <typename InT, int A, int G, bool SYM, bool UNPACKED, bool CS, int BITS>
 __global__ void __launch_bounds__(kV2Threads, (UNPACKED || CS) ? 2 : 3)
 group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out, V2ColScale csp) {
   static_assert(!CS || A == AR_F32, "column scaling is defined in fp32 arithmetic");
+  static_assert(BITS == 4 || BITS == 8, "int4 or int8 codes");
+  constexpr int NW = BITS;               // packed words per thread: 32 codes * BITS / 32
+  constexpr uint32_t CMAX = (1u << BITS) - 1u;
   constexpr int LPG = G / 32;            // lanes per group (4, 2, 1)
   const int LPW = LPG << out.zq_log2;    // lanes per packed zero-point word (8 groups: 32, 16, 8)
-  constexpr int QMIN = SYM ? -8 : 0;
-  constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + 15);
+  constexpr int QMIN = SYM ? -(1 << (BITS - 1)) : 0;
+  constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + (int)CMAX);
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kV2Stages * kV2StageBytes + (UNPACKED ? kV2UnpStageBytes : 0));
@@ -295,18 +329,18 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     ld_off[c] = smem_thr + (uint32_t)(((c + rot) & 3) << 4);
     asm volatile("" : "+r"(ld_off[c]));             // (no per-tile re-derivation from SR_CgaCtaId)
   }
-  uint8_t* const q_base = reinterpret_cast<uint8_t*>(out.q_packed + (e_first >> 3));
+  uint8_t* const q_base = reinterpret_cast<uint8_t*>(out.q_packed) + e_first * BITS / 8;
   uint8_t* const s_base = reinterpret_cast<uint8_t*>(out.scales + e_first / G);
   uint8_t* const z_base = reinterpret_cast<uint8_t*>(out.zp + e_first / G);
   uint8_t* const zq_base = reinterpret_cast<uint8_t*>(out.zp_packed + ((e_first / G) >> out.zq_log2));
-  const uint32_t q_step = (uint32_t)(e_stride >> 3) * 4u;          // bytes per iteration (< 2^32: grid <= 3*SMs)
+  const uint32_t q_step = (uint32_t)(e_stride * BITS / 8);         // bytes per iteration (< 2^32: grid <= 3*SMs)
   const uint32_t s_step = (uint32_t)(e_stride / G) * 2u;
   const uint32_t z_step = (uint32_t)(e_stride / G) * 4u;
   const uint32_t zq_step = (uint32_t)((e_stride / G) >> out.zq_log2) * 4u;
   const bool has_zp = out.zp != nullptr, has_zq = out.zp_packed != nullptr;
   const bool leader = (lane % LPG) == 0;
   const bool zq_writer = (lane & (LPW - 1)) == 0;
-  const uint32_t zq_shift = 4u * ((uint32_t)(lane / LPG) & ((1u << out.zq_log2) - 1u));
+  const uint32_t zq_shift = (uint32_t)BITS * ((uint32_t)(lane / LPG) & ((1u << out.zq_log2) - 1u));
   const uint32_t zq_mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
 
   // UNPACKED: warp-private staging of 256 x 16 B chunks.  Thread l owns logical chunks 8l..8l+7 (4 codes
@@ -340,7 +374,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     }
   }
 
-  PairQuant<A, QMIN> pq;
+  PairQuant<A, QMIN, BITS> pq;
   pq.prepare();
   uint32_t stage = 0, ph = 0;
   for (uint32_t it = 0; it < iters; ++it) {
@@ -395,16 +429,17 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
       mx = v2_fmax_nan(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
     }
 
-    const FastGroup fg = group_params_fast<A, 4>(mn, mx, SYM, FQMIN, FQMAX);
+    const FastGroup fg = group_params_fast<A, BITS>(mn, mx, SYM, FQMIN, FQMAX);
     float sc = fg.scale, zp = fg.zp;
-    uint32_t words[4];
+    uint32_t words[NW];              // BITS = 4: slot wi -> words[wi]; BITS = 8: slot wi -> words[2 wi], words[2 wi + 1]
     uint32_t nanmask = 0;            // UNPACKED: bit e <=> code of logical element e is NaN (INT32_MIN)
     // tighter than group_params_fast: the packed 16-bit clamp needs round(x/s + zp) inside the
     // range where the magic-constant add is linear and the s16 rebase cannot wrap
     //   fp32 : |x|/s < 2^14 (low half of the fp32 magic sum is an s16)
     //   bf16 : b + 192 must stay in [128, 256)  -> |x|/s < 48
     //   fp16 : b + 1536 must stay in [1024, 2048) -> |x|/s < 400
-    constexpr float LIM = (A == AR_F32) ? 16384.0f : ((A == AR_BF16) ? 48.0f : 400.0f);
+    //   8 bit: every mode rounds through the fp32 magic -> 2^14
+    constexpr float LIM = (A == AR_F32 || BITS == 8) ? 16384.0f : ((A == AR_BF16) ? 48.0f : 400.0f);
     const bool fast = fg.ok && (fmaxf(fabsf(mn), fabsf(mx)) < sc * LIM);
     if (fast) {
       pq.init(zp);
@@ -420,11 +455,16 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
           const float2 e = __ffma2_rn(ns2, q0, x);
           const float2 q = __ffma2_rn(e, r2, q0);                 // correctly rounded x / s
           const uint32_t u2 = pq.run(q);                          // (u_lo | u_hi << 16)
-          b3[p] = u2 * 0x01001000u;                               // byte 3 = u_lo | u_hi << 4
+          b3[p] = (BITS == 4) ? u2 * 0x01001000u : u2;            // int4: byte 3 = u_lo | u_hi << 4
         }
-        const uint32_t lo = __byte_perm(b3[0], b3[1], 0x0073);
-        const uint32_t hi = __byte_perm(b3[2], b3[3], 0x0073);
-        words[wi] = __byte_perm(lo, hi, 0x5410);
+        if (BITS == 4) {
+          const uint32_t lo = __byte_perm(b3[0], b3[1], 0x0073);
+          const uint32_t hi = __byte_perm(b3[2], b3[3], 0x0073);
+          words[wi * (NW / 4)] = __byte_perm(lo, hi, 0x5410);
+        } else {                                                  // int8: bytes 0 and 2 of each pair
+          words[wi * (NW / 4)] = __byte_perm(b3[0], b3[1], 0x6420);
+          words[wi * (NW / 4) + (NW / 4 - 1)] = __byte_perm(b3[2], b3[3], 0x6420);
+        }
       }
     } else {
       const GroupParams gp = group_params<A>(mn, mx, SYM, FQMIN, FQMAX);   // exact IEEE path
@@ -432,7 +472,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
       zp = gp.zp;
 #pragma unroll
       for (int wi = 0; wi < 4; ++wi) {
-        uint32_t acc = 0;
+        uint32_t acc = 0, acc2 = 0;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const float2 x = CS ? xv[4 * wi + p] : Packed<InT>::to_f2(wds[4 * wi + p]);
@@ -440,36 +480,64 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
           const int c1 = quant_exact<A>(x.y, sc, zp, FQMIN, FQMAX);
           const uint32_t u0 = (c0 == INT32_MIN) ? 0u : (uint32_t)(c0 - QMIN);
           const uint32_t u1 = (c1 == INT32_MIN) ? 0u : (uint32_t)(c1 - QMIN);
-          acc |= (u0 & 15u) << (8 * p);
-          acc |= (u1 & 15u) << (8 * p + 4);
+          if (BITS == 4) {
+            acc |= (u0 & 15u) << (8 * p);
+            acc |= (u1 & 15u) << (8 * p + 4);
+          } else if (p < 2) {
+            acc |= ((u0 & 255u) | ((u1 & 255u) << 8)) << (16 * p);
+          } else {
+            acc2 |= ((u0 & 255u) | ((u1 & 255u) << 8)) << (16 * (p - 2));
+          }
           if (UNPACKED) {            // slot wi holds logical 16-byte chunk (wi + rot) & 3
             const int e = 8 * ((wi + rot) & 3) + 2 * p;
             nanmask |= (c0 == INT32_MIN ? 1u : 0u) << e;
             nanmask |= (c1 == INT32_MIN ? 1u : 0u) << (e + 1);
           }
         }
-        words[wi] = acc;
+        words[wi * (NW / 4)] = acc;
+        if (BITS == 8) words[wi * (NW / 4) + (NW / 4 - 1)] = acc2;
       }
     }
 
     // ---- stores ------------------------------------------------------------------------------
     const int zi = f2i_x86(zp);
     // slot c holds chunk (c + rot) & 3  ->  chunk k sits in slot (k - rot) & 3: rotate left by rot
-    uint32_t o0 = words[0], o1 = words[1], o2 = words[2], o3 = words[3];
-    if (rot & 1) { const uint32_t t = o3; o3 = o2; o2 = o1; o1 = o0; o0 = t; }
-    if (rot & 2) { uint32_t t = o0; o0 = o2; o2 = t; t = o1; o1 = o3; o3 = t; }
-    if (valid && (!UNPACKED || has_qp)) st_stream16(q_base + (uint64_t)it * q_step, make_uint4(o0, o1, o2, o3));
+    // (a slot is one word for int4, two for int8: ow[h][k] = word h of chunk k)
+    uint32_t ow[NW / 4][4];
+#pragma unroll
+    for (int h = 0; h < NW / 4; ++h) {
+      uint32_t o0 = words[h], o1 = words[(NW / 4) + h], o2 = words[2 * (NW / 4) + h], o3 = words[3 * (NW / 4) + h];
+      if (rot & 1) { const uint32_t t = o3; o3 = o2; o2 = o1; o1 = o0; o0 = t; }
+      if (rot & 2) { uint32_t t = o0; o0 = o2; o2 = t; t = o1; o1 = o3; o3 = t; }
+      ow[h][0] = o0; ow[h][1] = o1; ow[h][2] = o2; ow[h][3] = o3;
+    }
+    if (valid && (!UNPACKED || has_qp)) {
+      uint8_t* dst = q_base + (uint64_t)it * q_step;
+      if (BITS == 4) {
+        st_stream16(dst, make_uint4(ow[0][0], ow[0][1], ow[0][2], ow[0][3]));
+      } else {
+        st_stream16(dst, make_uint4(ow[0][0], ow[NW / 4 - 1][0], ow[0][1], ow[NW / 4 - 1][1]));
+        st_stream16(dst + 16, make_uint4(ow[0][2], ow[NW / 4 - 1][2], ow[0][3], ow[NW / 4 - 1][3]));
+      }
+    }
     if (UNPACKED) {
-      const uint32_t ow[4] = {o0, o1, o2, o3};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        // 8 nibbles -> 8 int32 codes: even nibbles / odd nibbles to bytes, then one PRMT per code
-        const uint32_t ev = ow[k] & 0x0F0F0F0Fu, od = (ow[k] >> 4) & 0x0F0F0F0Fu;
         int c[8];
-        c[0] = (int)__byte_perm(ev, 0u, 0x4440) + QMIN; c[1] = (int)__byte_perm(od, 0u, 0x4440) + QMIN;
-        c[2] = (int)__byte_perm(ev, 0u, 0x4441) + QMIN; c[3] = (int)__byte_perm(od, 0u, 0x4441) + QMIN;
-        c[4] = (int)__byte_perm(ev, 0u, 0x4442) + QMIN; c[5] = (int)__byte_perm(od, 0u, 0x4442) + QMIN;
-        c[6] = (int)__byte_perm(ev, 0u, 0x4443) + QMIN; c[7] = (int)__byte_perm(od, 0u, 0x4443) + QMIN;
+        if (BITS == 4) {
+          // 8 nibbles -> 8 int32 codes: even nibbles / odd nibbles to bytes, then one PRMT per code
+          const uint32_t ev = ow[0][k] & 0x0F0F0F0Fu, od = (ow[0][k] >> 4) & 0x0F0F0F0Fu;
+          c[0] = (int)__byte_perm(ev, 0u, 0x4440) + QMIN; c[1] = (int)__byte_perm(od, 0u, 0x4440) + QMIN;
+          c[2] = (int)__byte_perm(ev, 0u, 0x4441) + QMIN; c[3] = (int)__byte_perm(od, 0u, 0x4441) + QMIN;
+          c[4] = (int)__byte_perm(ev, 0u, 0x4442) + QMIN; c[5] = (int)__byte_perm(od, 0u, 0x4442) + QMIN;
+          c[6] = (int)__byte_perm(ev, 0u, 0x4443) + QMIN; c[7] = (int)__byte_perm(od, 0u, 0x4443) + QMIN;
+        } else {
+          const uint32_t w0 = ow[0][k], w1 = ow[NW / 4 - 1][k];
+          c[0] = (int)__byte_perm(w0, 0u, 0x4440) + QMIN; c[1] = (int)__byte_perm(w0, 0u, 0x4441) + QMIN;
+          c[2] = (int)__byte_perm(w0, 0u, 0x4442) + QMIN; c[3] = (int)__byte_perm(w0, 0u, 0x4443) + QMIN;
+          c[4] = (int)__byte_perm(w1, 0u, 0x4440) + QMIN; c[5] = (int)__byte_perm(w1, 0u, 0x4441) + QMIN;
+          c[6] = (int)__byte_perm(w1, 0u, 0x4442) + QMIN; c[7] = (int)__byte_perm(w1, 0u, 0x4443) + QMIN;
+        }
         if (nanmask != 0) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -495,14 +563,14 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
       if (has_zp) *reinterpret_cast<int32_t*>(z_base + (uint64_t)it * z_step) = zi;
     }
     if (has_zq) {
-      const uint32_t uz = (valid && leader && zi != INT32_MIN) ? ((uint32_t)(zi - QMIN) & 15u) : 0u;
+      const uint32_t uz = (valid && leader && zi != INT32_MIN) ? ((uint32_t)(zi - QMIN) & CMAX) : 0u;
       const uint32_t wordz = __reduce_or_sync(zq_mask, uz << zq_shift);
       if (valid && zq_writer) *reinterpret_cast<uint32_t*>(zq_base + (uint64_t)it * zq_step) = wordz;
     }
   }
 }
 
-template <typename InT, int A, int G, bool UNPACKED, bool CS>
+template <typename InT, int A, int G, bool UNPACKED, bool CS, int BITS>
 static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, V2ColScale csp, cudaStream_t st) {
   int dev = 0, sms = 0;
   AWQK_CUDA(cudaGetDevice(&dev));
@@ -529,11 +597,11 @@ static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, V2ColScal
   const uint64_t bit = 1ull << (dev & 63);
   const bool need = !(configured[sym ? 1 : 0].load(std::memory_order_acquire) & bit);
   if (sym) {
-    auto k = group_quant_tma<InT, A, G, true, UNPACKED, CS>;
+    auto k = group_quant_tma<InT, A, G, true, UNPACKED, CS, BITS>;
     if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out, csp);
   } else {
-    auto k = group_quant_tma<InT, A, G, false, UNPACKED, CS>;
+    auto k = group_quant_tma<InT, A, G, false, UNPACKED, CS, BITS>;
     if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out, csp);
   }
@@ -542,38 +610,44 @@ static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, V2ColScal
   return AWQK_OK;
 }
 
-template <typename InT, int A, bool CS>
+template <typename InT, int A, bool CS, int BITS>
 static int launch_v2_g(const InT* w, int64_t n, int g, bool sym, V2Out out, V2ColScale csp, cudaStream_t st) {
   if (out.q_unpacked != nullptr) {
     switch (g) {
-      case 32: return launch_v2_sym<InT, A, 32, true, CS>(w, n, sym, out, csp, st);
-      case 64: return launch_v2_sym<InT, A, 64, true, CS>(w, n, sym, out, csp, st);
-      default: return launch_v2_sym<InT, A, 128, true, CS>(w, n, sym, out, csp, st);
+      case 32: return launch_v2_sym<InT, A, 32, true, CS, BITS>(w, n, sym, out, csp, st);
+      case 64: return launch_v2_sym<InT, A, 64, true, CS, BITS>(w, n, sym, out, csp, st);
+      default: return launch_v2_sym<InT, A, 128, true, CS, BITS>(w, n, sym, out, csp, st);
     }
   }
   switch (g) {
-    case 32: return launch_v2_sym<InT, A, 32, false, CS>(w, n, sym, out, csp, st);
-    case 64: return launch_v2_sym<InT, A, 64, false, CS>(w, n, sym, out, csp, st);
-    default: return launch_v2_sym<InT, A, 128, false, CS>(w, n, sym, out, csp, st);
+    case 32: return launch_v2_sym<InT, A, 32, false, CS, BITS>(w, n, sym, out, csp, st);
+    case 64: return launch_v2_sym<InT, A, 64, false, CS, BITS>(w, n, sym, out, csp, st);
+    default: return launch_v2_sym<InT, A, 128, false, CS, BITS>(w, n, sym, out, csp, st);
   }
 }
 
-// Entry used by awqk_group_quant: int4, bf16/fp16 input, flat layout (K % g == 0, g in {32,64,128},
-// 16-byte aligned base).  zp_packed: zq_log2 = 3 when a row is a whole number of 8-group words (G % 8 == 0),
-// 0/1/2 when a row is 1/2/4 groups (one word per row); otherwise it must be null.
-int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, bool sym, int arith,
+template <typename InT, int A>
+static int launch_v2_bits(const InT* w, int64_t n, int g, int bits, bool sym, V2Out out, cudaStream_t st) {
+  const V2ColScale none{nullptr, 0, 0, 0, 0};
+  return bits == 8 ? launch_v2_g<InT, A, false, 8>(w, n, g, sym, out, none, st)
+                   : launch_v2_g<InT, A, false, 4>(w, n, g, sym, out, none, st);
+}
+
+// Entry used by awqk_group_quant: int4 / int8, bf16/fp16 input, flat layout (K % g == 0, g in {32,64,128},
+// 16-byte aligned base).  zp_packed: zq_log2 = log2(32 / bits) when a row is a whole number of packed words,
+// smaller when a row is 1 / 2 / 4 groups (one zero-padded word per row); otherwise it must be null.
+int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, int bits, bool sym, int arith,
                            uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                            int zq_log2, cudaStream_t st) {
   V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed, zq_log2};
-  const V2ColScale none{nullptr, 0, 0, 0, 0};
   if (dtype == AWQK_BF16) {
     auto p = reinterpret_cast<const __nv_bfloat16*>(w);
-    return arith == AWQK_ARITH_FP32 ? launch_v2_g<__nv_bfloat16, AR_F32, false>(p, n_elems, g, sym, out, none, st)
-                                    : launch_v2_g<__nv_bfloat16, AR_BF16, false>(p, n_elems, g, sym, out, none, st);
+    return arith == AWQK_ARITH_FP32 ? launch_v2_bits<__nv_bfloat16, AR_F32>(p, n_elems, g, bits, sym, out, st)
+                                    : launch_v2_bits<__nv_bfloat16, AR_BF16>(p, n_elems, g, bits, sym, out, st);
   }
   auto p = reinterpret_cast<const __half*>(w);
-  return arith == AWQK_ARITH_FP32 ? launch_v2_g<__half, AR_F32, false>(p, n_elems, g, sym, out, none, st)
-                                  : launch_v2_g<__half, AR_F16, false>(p, n_elems, g, sym, out, none, st);
+  return arith == AWQK_ARITH_FP32 ? launch_v2_bits<__half, AR_F32>(p, n_elems, g, bits, sym, out, st)
+                                  : launch_v2_bits<__half, AR_F16>(p, n_elems, g, bits, sym, out, st);
 }
 
 // Column-scaled entry (col_scale != nullptr, fp32 arithmetic): needs K % 1024 == 0 and the per-iteration
@@ -589,8 +663,8 @@ int launch_group_quant_tma_cs(const void* w, int dtype, int64_t C, int64_t K, in
   V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed, 3};
   const V2ColScale csp{col_scale, K, C, 0, 0};
   if (dtype == AWQK_BF16)
-    return launch_v2_g<__nv_bfloat16, AR_F32, true>(reinterpret_cast<const __nv_bfloat16*>(w), C * K, g, sym, out, csp, st);
-  return launch_v2_g<__half, AR_F32, true>(reinterpret_cast<const __half*>(w), C * K, g, sym, out, csp, st);
+    return launch_v2_g<__nv_bfloat16, AR_F32, true, 4>(reinterpret_cast<const __nv_bfloat16*>(w), C * K, g, sym, out, csp, st);
+  return launch_v2_g<__half, AR_F32, true, 4>(reinterpret_cast<const __half*>(w), C * K, g, sym, out, csp, st);
 }
 
 }  // namespace awqk

@@ -542,3 +542,43 @@ def test_rows_of_1_2_4_groups_pack_zero_words_in_kernel(native_lib, cuda_device,
             assert_same(qp.cpu(), want["qweight"], f"{C}x{K}/g{g}/qweight")
             assert_same(sc.cpu(), want["scales"], f"{C}x{K}/g{g}/scales")
             assert_same(zq.cpu(), want["qzeros"], f"{C}x{K}/g{g}/qzeros")
+
+
+@pytest.mark.parametrize("dt", ["bf16", "fp16"])
+@pytest.mark.parametrize("arith", ["native", "fp32"])
+@pytest.mark.parametrize("sym", [False, True])
+def test_int8_through_tma_kernel(native_lib, cuda_device, dt, arith, sym):
+    """bits = 8 on the TMA path: packed words of 4 codes, 4 zero points per word (1- and 2-group rows packed in the
+    kernel), the reference's int32 codes, special values, magnitudes that push groups onto the exact path"""
+    from awq_quantizer import _native as N
+    ar = N.ARITH_FP32 if arith == "fp32" else N.ARITH_NATIVE
+    for (C, K), g, scale in (((40, 1024), 128, 0.02), ((9, 256), 128, 1.0), ((33, 128), 128, 300.0), ((16, 64), 32, 0.02),
+                             ((130, 512), 64, 1e-3), ((7, 4096), 32, 5.0)):
+        w = datagen.weights((C, K), "fp32", datagen.seed_of("i8", C, K, g), std=scale, offset=0.1 * scale)
+        w[0, :g] = 0.0
+        w[1, 0] = float("nan")
+        w[2, 1] = float("inf")
+        w[3, :g] = 0.75 * scale
+        w = w.to(datagen.DTYPES[dt])
+        G = K // g
+        wd = w.to(cuda_device)
+        q = torch.full((C, K), 9, dtype=torch.int32, device=cuda_device)
+        qp = torch.full((C, K // 4), 9, dtype=torch.int32, device=cuda_device)
+        sc = torch.zeros((C, G), dtype=torch.float16, device=cuda_device)
+        zp = torch.full((C, G), 9, dtype=torch.int32, device=cuda_device)
+        zq = torch.full((C, -(-G // 4)), 9, dtype=torch.int32, device=cuda_device)
+        needs_zp = G % 4 != 0 and G not in (1, 2)
+        for unpacked in (False, True):
+            rc = native_lib.awqk_group_quant(wd.data_ptr(), N.dtype_code(w.dtype), C, K, g, 8, int(sym), ar,
+                                             q.data_ptr() if unpacked else None, qp.data_ptr(), sc.data_ptr(),
+                                             zp.data_ptr() if (unpacked or needs_zp) else None, zq.data_ptr(), None, None)
+            assert rc == 0, (rc, C, K, g)
+            torch.cuda.synchronize()
+            want = O.pack_result(O.group_quant_vec(w, 8, g, sym, True, arith=arith))
+            what = f"{C}x{K}/g{g}/{unpacked}"
+            assert_same(qp.cpu(), want["qweight"], what + "/qweight")
+            assert_same(sc.cpu(), want["scales"], what + "/scales")
+            assert_same(zq.cpu(), want["qzeros"], what + "/qzeros")
+            if unpacked:
+                assert_same(q.cpu(), want["tensor_q"], what + "/tensor_q")
+                assert_same(zp.cpu(), want["zero_points"].reshape(C, G), what + "/zero_points")
