@@ -502,7 +502,7 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
   QuantOut out{q_unpacked, q_packed, reinterpret_cast<__half*>(scales_f16), zp, zp_packed};
 
   if (path == 1) {
-    const bool tma_plain = (dtype == AWQK_BF16 || dtype == AWQK_FP16) &&
+    const bool tma_plain = (dtype == AWQK_BF16 || dtype == AWQK_FP16 || (dtype == AWQK_FP32 && bits == 4)) &&
                            (q_packed != nullptr || q_unpacked != nullptr) && col_scale == nullptr && tma_path_enabled() &&
                            (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0;
     // rows of 1 / 2 / 4 groups (fewer than a packed word): K1 v2 writes one zero-padded word per row itself

@@ -25,7 +25,6 @@ constexpr int kV2Threads = (kV2ConsumerWarps + 1) * 32;   // + 1 producer warp
 constexpr int kV2WarpTile = 1024;                         // elements
 constexpr int kV2CtaTile = kV2WarpTile * kV2ConsumerWarps;  // 8192 elements = 16 KiB
 constexpr int kV2Stages = 4;
-constexpr int kV2StageBytes = kV2CtaTile * 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -94,6 +93,14 @@ struct Packed<__half> {
   static __device__ __forceinline__ float2 to_f2(uint32_t w) {
     return __half22float2(*reinterpret_cast<V2*>(&w));
   }
+};
+
+// fp32 input never takes the packed 16-bit paths; these only keep the discarded branches well-formed
+template <>
+struct Packed<float> {
+  static __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t) { return a; }
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t) { return a; }
+  static __device__ __forceinline__ float2 to_f2(uint32_t w) { return make_float2(__uint_as_float(w), 0.0f); }
 };
 
 __device__ __forceinline__ float v2_fmin_nan(float a, float b) {
@@ -235,10 +242,18 @@ __device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
 }
 
 template <typename InT, int A, int G, bool SYM, bool UNPACKED, bool CS, int BITS>
-__global__ void __launch_bounds__(kV2Threads, (UNPACKED || CS) ? 2 : 3)
+__global__ void __launch_bounds__(kV2Threads, (UNPACKED || CS || sizeof(InT) == 4) ? 2 : 3)
 group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out, V2ColScale csp) {
   static_assert(!CS || A == AR_F32, "column scaling is defined in fp32 arithmetic");
   static_assert(BITS == 4 || BITS == 8, "int4 or int8 codes");
+  // fp32 input: a thread's 32 elements are 128 B = 8 LDS.128; stages are 32 KiB, so 3 of them (2 with the
+  // UNPACKED staging) keep 2 CTAs per SM.  Chunk c of the thread's span is read into slot c ^ (lane & 7)
+  // (conflict-free: a quarter warp covers all 8 bank groups); slots 2w, 2w+1 still hold the two halves of one
+  // packed word, swapped for odd lanes.
+  constexpr bool F32IN = sizeof(InT) == 4;
+  static_assert(!F32IN || (A == AR_F32 && !CS && BITS == 4), "fp32 input: fp32 arithmetic, flat mode, int4");
+  constexpr int STAGES = F32IN ? (UNPACKED ? 2 : 3) : kV2Stages;
+  constexpr uint32_t STAGE_BYTES = kV2CtaTile * sizeof(InT);
   constexpr int NW = BITS;               // packed words per thread: 32 codes * BITS / 32
   constexpr uint32_t CMAX = (1u << BITS) - 1u;
   constexpr int LPG = G / 32;            // lanes per group (4, 2, 1)
@@ -247,16 +262,16 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + (int)CMAX);
 
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kV2Stages * kV2StageBytes + (UNPACKED ? kV2UnpStageBytes : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (UNPACKED ? kV2UnpStageBytes : 0));
   uint32_t full0 = smem_u32(bars);
-  uint32_t empty0 = smem_u32(bars + kV2Stages);
+  uint32_t empty0 = smem_u32(bars + STAGES);
   asm volatile("" : "+r"(full0), "+r"(empty0));   // keep the shared-window addresses in registers
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kV2Stages; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, kV2ConsumerWarps);
     }
@@ -283,29 +298,29 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
           mbar_wait(empty0 + 8 * stage, ph);
           const int rows = rows_left < kV2ConsumerWarps ? (int)rows_left : kV2ConsumerWarps;
           mbar_expect_tx(full0 + 8 * stage, (uint32_t)rows * (kV2WarpTile * 2));
-          const uint32_t dst = smem_u32(smem) + stage * kV2StageBytes;
+          const uint32_t dst = smem_u32(smem) + stage * STAGE_BYTES;
           for (int r = 0; r < rows; ++r)
             bulk_g2s(dst + r * (kV2WarpTile * 2), src + r * row_bytes, kV2WarpTile * 2, full0 + 8 * stage);
           src += src_stride;
           rows_left -= tile_step * kV2ConsumerWarps;
-          if (++stage == kV2Stages) { stage = 0; ph ^= 1u; }
+          if (++stage == STAGES) { stage = 0; ph ^= 1u; }
         }
       }
       return;
     }
     if (lane == 0) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(w) + tile0 * kV2StageBytes;
-      const int64_t src_stride = (int64_t)gridDim.x * kV2StageBytes;
-      int64_t left = n_elems * 2 - tile0 * kV2StageBytes;          // bytes from this tile to the end
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(w) + tile0 * STAGE_BYTES;
+      const int64_t src_stride = (int64_t)gridDim.x * STAGE_BYTES;
+      int64_t left = n_elems * (int64_t)sizeof(InT) - tile0 * STAGE_BYTES;          // bytes from this tile to the end
       uint32_t stage = 0, ph = 1;                                   // first pass over the ring: slots are free
       for (int64_t it = 0; it < n_iters; ++it) {
         mbar_wait(empty0 + 8 * stage, ph);
-        const uint32_t bytes = (left < kV2StageBytes) ? (uint32_t)left : (uint32_t)kV2StageBytes;
+        const uint32_t bytes = (left < STAGE_BYTES) ? (uint32_t)left : (uint32_t)STAGE_BYTES;
         mbar_expect_tx(full0 + 8 * stage, bytes);
-        bulk_g2s(smem_u32(smem) + stage * kV2StageBytes, src, bytes, full0 + 8 * stage);
+        bulk_g2s(smem_u32(smem) + stage * STAGE_BYTES, src, bytes, full0 + 8 * stage);
         src += src_stride;
         left -= src_stride;
-        if (++stage == kV2Stages) { stage = 0; ph ^= 1u; }
+        if (++stage == STAGES) { stage = 0; ph ^= 1u; }
       }
     }
     return;
@@ -321,14 +336,20 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   const uint32_t iters = (uint32_t)n_iters;
   // iterations in which this thread's 32 elements exist (whole groups are valid or not)
   const uint32_t valid_iters = (n_elems > e_first) ? (uint32_t)((n_elems - e_first + e_stride - 1) / e_stride) : 0u;
+  // rot: bf16/fp16 -> slot c holds chunk (c + rot) & 3; fp32 -> word slot wp holds word wp ^ rot
   const int rot = (lane >> 1) & 3;
-  const uint32_t smem_thr = smem_u32(smem) + (uint32_t)warp * (kV2WarpTile * 2) + (uint32_t)lane * 64u;
-  uint32_t ld_off[4];
+  const uint32_t smem_thr = smem_u32(smem) + (uint32_t)warp * (kV2WarpTile * (uint32_t)sizeof(InT)) +
+                            (uint32_t)lane * (32u * (uint32_t)sizeof(InT));
+  constexpr int NLD = F32IN ? 8 : 4;                // LDS.128 per thread and tile
+  uint32_t ld_off[NLD];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    ld_off[c] = smem_thr + (uint32_t)(((c + rot) & 3) << 4);
+  for (int c = 0; c < NLD; ++c) {
+    ld_off[c] = smem_thr + (uint32_t)((F32IN ? (c ^ (lane & 7)) : ((c + rot) & 3)) << 4);
     asm volatile("" : "+r"(ld_off[c]));             // (no per-tile re-derivation from SR_CgaCtaId)
   }
+  // fp32 input: half-word merge selector (even lanes: slot 2w is the low half of word w; odd lanes: the high half)
+  const uint32_t half_sel = (F32IN && (lane & 1)) ? 0x1054u : 0x5410u;
+  const int odd_shift = (F32IN && (lane & 1)) ? 2 : 0;
   uint8_t* const q_base = reinterpret_cast<uint8_t*>(out.q_packed) + e_first * BITS / 8;
   uint8_t* const s_base = reinterpret_cast<uint8_t*>(out.scales + e_first / G);
   uint8_t* const z_base = reinterpret_cast<uint8_t*>(out.zp + e_first / G);
@@ -349,7 +370,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   uint8_t* qu_base = nullptr;
   const bool has_qp = out.q_packed != nullptr;
   if (UNPACKED) {
-    const uint32_t stg0 = smem_u32(smem) + kV2Stages * kV2StageBytes + (uint32_t)warp * (kV2WarpTile * 4);
+    const uint32_t stg0 = smem_u32(smem) + STAGES * STAGE_BYTES + (uint32_t)warp * (kV2WarpTile * 4);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       stg_w[j] = stg0 + (uint32_t)((8 * lane + (j ^ (lane & 7))) << 4);
@@ -384,25 +405,27 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     // thread's span: rotating the chunk order by lane/2 makes every quarter-warp hit 8 distinct
     // bank groups.  Min/max and the per-word quantization are order independent; only the final
     // 16-byte store has to rotate the 4 result words back (8 SELs).
-    uint32_t wds[16];
+    uint32_t wds[4 * NLD];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < NLD; ++c) {
       asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                    : "=r"(wds[4 * c]), "=r"(wds[4 * c + 1]), "=r"(wds[4 * c + 2]), "=r"(wds[4 * c + 3])
-                   : "r"(ld_off[c] + stage * kV2StageBytes));
+                   : "r"(ld_off[c] + stage * STAGE_BYTES));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * stage);   // slot is free as soon as it sits in registers
-    if (++stage == kV2Stages) { stage = 0; ph ^= 1u; }
+    if (++stage == STAGES) { stage = 0; ph ^= 1u; }
     // (threads past the end of the tensor compute on stale shared memory and store nothing)
 
     // ---- group min / max: packed tree over 16 words, then fold halves, then LPG lanes --------
     float mn, mx;
-    float2 xv[CS ? 16 : 1];
-    if (CS) {
-      // x = fp32(w) * s[k]; the group statistics are taken on x (3-input FMNMX)
+    float2 xv[(CS || F32IN) ? 16 : 1];
+    if (CS || F32IN) {
+      // CS: x = fp32(w) * s[k]; fp32 input: x = w.  The group statistics are taken on x (3-input FMNMX)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) xv[i] = __fmul2_rn(Packed<InT>::to_f2(wds[i]), sreg[i]);
+      for (int i = 0; i < 16; ++i)
+        xv[i] = F32IN ? make_float2(__uint_as_float(wds[(2 * i) % (4 * NLD)]), __uint_as_float(wds[(2 * i + 1) % (4 * NLD)]))
+                      : __fmul2_rn(Packed<InT>::to_f2(wds[i % (4 * NLD)]), sreg[CS ? i : 0]);
       mn = fmin3_nan(xv[0].x, xv[0].y, xv[1].x);
       mx = fmax3_nan(xv[0].x, xv[0].y, xv[1].x);
       mn = v2_fmin_nan(mn, xv[1].y);
@@ -450,7 +473,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
         uint32_t b3[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const float2 x = CS ? xv[4 * wi + p] : Packed<InT>::to_f2(wds[4 * wi + p]);
+          const float2 x = (CS || F32IN) ? xv[(CS || F32IN) ? 4 * wi + p : 0] : Packed<InT>::to_f2(wds[4 * wi + p]);
           const float2 q0 = __fmul2_rn(x, r2);
           const float2 e = __ffma2_rn(ns2, q0, x);
           const float2 q = __ffma2_rn(e, r2, q0);                 // correctly rounded x / s
@@ -460,7 +483,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
         if (BITS == 4) {
           const uint32_t lo = __byte_perm(b3[0], b3[1], 0x0073);
           const uint32_t hi = __byte_perm(b3[2], b3[3], 0x0073);
-          words[wi * (NW / 4)] = __byte_perm(lo, hi, 0x5410);
+          words[wi * (NW / 4)] = __byte_perm(lo, hi, half_sel);
         } else {                                                  // int8: bytes 0 and 2 of each pair
           words[wi * (NW / 4)] = __byte_perm(b3[0], b3[1], 0x6420);
           words[wi * (NW / 4) + (NW / 4 - 1)] = __byte_perm(b3[2], b3[3], 0x6420);
@@ -475,21 +498,21 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
         uint32_t acc = 0, acc2 = 0;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const float2 x = CS ? xv[4 * wi + p] : Packed<InT>::to_f2(wds[4 * wi + p]);
+          const float2 x = (CS || F32IN) ? xv[(CS || F32IN) ? 4 * wi + p : 0] : Packed<InT>::to_f2(wds[4 * wi + p]);
           const int c0 = quant_exact<A>(x.x, sc, zp, FQMIN, FQMAX);
           const int c1 = quant_exact<A>(x.y, sc, zp, FQMIN, FQMAX);
           const uint32_t u0 = (c0 == INT32_MIN) ? 0u : (uint32_t)(c0 - QMIN);
           const uint32_t u1 = (c1 == INT32_MIN) ? 0u : (uint32_t)(c1 - QMIN);
           if (BITS == 4) {
-            acc |= (u0 & 15u) << (8 * p);
-            acc |= (u1 & 15u) << (8 * p + 4);
+            acc |= (u0 & 15u) << (8 * (p ^ odd_shift));
+            acc |= (u1 & 15u) << (8 * (p ^ odd_shift) + 4);
           } else if (p < 2) {
             acc |= ((u0 & 255u) | ((u1 & 255u) << 8)) << (16 * p);
           } else {
             acc2 |= ((u0 & 255u) | ((u1 & 255u) << 8)) << (16 * (p - 2));
           }
-          if (UNPACKED) {            // slot wi holds logical 16-byte chunk (wi + rot) & 3
-            const int e = 8 * ((wi + rot) & 3) + 2 * p;
+          if (UNPACKED) {            // slot wi holds logical 16-byte chunk (wi + rot) & 3  (fp32: word wi ^ rot)
+            const int e = F32IN ? 8 * (wi ^ rot) + 2 * (p ^ odd_shift) : 8 * ((wi + rot) & 3) + 2 * p;
             nanmask |= (c0 == INT32_MIN ? 1u : 0u) << e;
             nanmask |= (c1 == INT32_MIN ? 1u : 0u) << (e + 1);
           }
@@ -507,7 +530,11 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
 #pragma unroll
     for (int h = 0; h < NW / 4; ++h) {
       uint32_t o0 = words[h], o1 = words[(NW / 4) + h], o2 = words[2 * (NW / 4) + h], o3 = words[3 * (NW / 4) + h];
-      if (rot & 1) { const uint32_t t = o3; o3 = o2; o2 = o1; o1 = o0; o0 = t; }
+      if (F32IN) {                 // word slot wp holds word wp ^ rot
+        if (rot & 1) { uint32_t t = o0; o0 = o1; o1 = t; t = o2; o2 = o3; o3 = t; }
+      } else {
+        if (rot & 1) { const uint32_t t = o3; o3 = o2; o2 = o1; o1 = o0; o0 = t; }
+      }
       if (rot & 2) { uint32_t t = o0; o0 = o2; o2 = t; t = o1; o1 = o3; o3 = t; }
       ow[h][0] = o0; ow[h][1] = o1; ow[h][2] = o2; ow[h][3] = o3;
     }
@@ -575,7 +602,7 @@ static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, V2ColScal
   int dev = 0, sms = 0;
   AWQK_CUDA(cudaGetDevice(&dev));
   AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t want = (int64_t)sms * ((UNPACKED || CS) ? 2 : 3);   // resident CTAs per SM (smem / register bound)
+  const int64_t want = (int64_t)sms * ((UNPACKED || CS || sizeof(InT) == 4) ? 2 : 3);   // resident CTAs per SM (smem / register bound)
   int64_t n_tiles;
   unsigned grid;
   if (CS) {
@@ -591,7 +618,9 @@ static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, V2ColScal
     n_tiles = ceil_div(n, kV2CtaTile);
     grid = (unsigned)(n_tiles < want ? n_tiles : want);
   }
-  const size_t smem = (size_t)kV2Stages * kV2StageBytes + (UNPACKED ? kV2UnpStageBytes : 0) + 2 * kV2Stages * sizeof(uint64_t);
+  constexpr bool F32IN = sizeof(InT) == 4;                         // (same constants as in the kernel)
+  constexpr int STAGES = F32IN ? (UNPACKED ? 2 : 3) : kV2Stages;
+  const size_t smem = (size_t)STAGES * kV2CtaTile * sizeof(InT) + (UNPACKED ? kV2UnpStageBytes : 0) + 2 * STAGES * sizeof(uint64_t);
   // the dynamic-smem opt-in is per (kernel instantiation, device): set once, then immutable
   static std::atomic<uint64_t> configured[2] = {{0}, {0}};
   const uint64_t bit = 1ull << (dev & 63);
@@ -644,6 +673,10 @@ int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, int
     auto p = reinterpret_cast<const __nv_bfloat16*>(w);
     return arith == AWQK_ARITH_FP32 ? launch_v2_bits<__nv_bfloat16, AR_F32>(p, n_elems, g, bits, sym, out, st)
                                     : launch_v2_bits<__nv_bfloat16, AR_BF16>(p, n_elems, g, bits, sym, out, st);
+  }
+  if (dtype == AWQK_FP32) {           // int4 only (the dispatcher keeps 8-bit fp32 input on the register path)
+    const V2ColScale none{nullptr, 0, 0, 0, 0};
+    return launch_v2_g<float, AR_F32, false, 4>(reinterpret_cast<const float*>(w), n_elems, g, sym, out, none, st);
   }
   auto p = reinterpret_cast<const __half*>(w);
   return arith == AWQK_ARITH_FP32 ? launch_v2_bits<__half, AR_F32>(p, n_elems, g, bits, sym, out, st)

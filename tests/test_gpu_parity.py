@@ -582,3 +582,39 @@ def test_int8_through_tma_kernel(native_lib, cuda_device, dt, arith, sym):
             if unpacked:
                 assert_same(q.cpu(), want["tensor_q"], what + "/tensor_q")
                 assert_same(zp.cpu(), want["zero_points"].reshape(C, G), what + "/zero_points")
+
+
+@pytest.mark.parametrize("sym", [False, True])
+@pytest.mark.parametrize("g", [32, 64, 128])
+def test_fp32_input_through_tma_kernel(native_lib, cuda_device, sym, g):
+    """fp32 weights on the TMA path (8 LDS.128 per thread, XOR-swizzled chunk order, halves of a packed word swapped on
+    odd lanes): packed words, int32 codes, zero points, special values, partial tiles, many tiles per CTA"""
+    from awq_quantizer import _native as N
+    for (C, K), scale in (((40, 1024), 0.02), ((3, 128 * 7), 1.0), ((600, 8192), 0.02), ((33, 2048), 1e-20), ((9, 512), 3e4)):
+        w = datagen.weights((C, K), "fp32", datagen.seed_of("f32tma", C, K, g), std=scale, offset=0.3 * scale)
+        w[0, :g] = 0.0
+        w[1, 5] = float("nan")
+        w[2, 77] = float("-inf")
+        w[-1, -g:] = 1.25 * scale
+        G = K // g
+        wd = w.to(cuda_device)
+        q = torch.full((C, K), 9, dtype=torch.int32, device=cuda_device)
+        qp = torch.full((C, K // 8), 9, dtype=torch.int32, device=cuda_device)
+        sc = torch.zeros((C, G), dtype=torch.float16, device=cuda_device)
+        zp = torch.full((C, G), 9, dtype=torch.int32, device=cuda_device)
+        flat_zq = G % 8 == 0 or G in (1, 2, 4)
+        zq = torch.full((C, -(-G // 8)), 9, dtype=torch.int32, device=cuda_device)
+        want = O.pack_result(O.group_quant_vec(w, 4, g, sym, True))
+        for unpacked in (False, True):
+            rc = native_lib.awqk_group_quant(wd.data_ptr(), N.FP32, C, K, g, 4, int(sym), N.ARITH_NATIVE,
+                                             q.data_ptr() if unpacked else None, qp.data_ptr(), sc.data_ptr(),
+                                             zp.data_ptr() if (unpacked or not flat_zq) else None, zq.data_ptr(), None, None)
+            assert rc == 0, (rc, C, K, g)
+            torch.cuda.synchronize()
+            what = f"{C}x{K}/g{g}/{unpacked}"
+            assert_same(qp.cpu(), want["qweight"], what + "/qweight")
+            assert_same(sc.cpu(), want["scales"], what + "/scales")
+            assert_same(zq.cpu(), want["qzeros"], what + "/qzeros")
+            if unpacked:
+                assert_same(q.cpu(), want["tensor_q"], what + "/tensor_q")
+                assert_same(zp.cpu(), want["zero_points"].reshape(C, G), what + "/zero_points")
