@@ -435,6 +435,12 @@ def run_native(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line (the JSON record): libraries that write to file descriptor 1 behind Python's
+    # back (NCCL prints its version banner there when NCCL_DEBUG is set in the environment) are sent to stderr.
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_out, "w", buffering=1)
     if args.impl == "reference":
         return run_reference(args)
     return run_native(args)
