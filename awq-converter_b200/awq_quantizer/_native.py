@@ -56,6 +56,15 @@ def lib() -> C.CDLL:
     if _lib is None:
         with _lock:
             if _lib is None:
+                if "AWQK_PIPE_THREADS" not in os.environ:
+                    # one process per GPU (torchrun): the ranks share the host's cores -- size the pipeline's
+                    # staging-copy pool accordingly (the library reads the variable once, at first use)
+                    try:
+                        ranks = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+                    except ValueError:
+                        ranks = 1
+                    if ranks > 1:
+                        os.environ["AWQK_PIPE_THREADS"] = str(max(2, min(8, (os.cpu_count() or 8) // ranks)))
                 if not os.path.exists(LIB_PATH):
                     raise NativeError(
                         f"{LIB_PATH} not found: build it with `python awq-converter_b200/build.py` "

@@ -98,6 +98,18 @@ class HostArena:
         return sum(n * torch.empty((), dtype=dt).element_size() for dt, lay in self.layout.items() for _, _, n in lay)
 
 
+class _ThreadPipes(dict):
+    """the pipes of one host thread; destroyed (streams, device slots, pinned rings) when the thread goes away"""
+
+    def __del__(self):
+        try:
+            L = N.lib()
+            for handle in self.values():
+                L.awqk_pipe_destroy(handle)
+        except Exception:       # interpreter shutdown
+            pass
+
+
 class _PipeHandle:
     """per-thread, per-device awqk_pipe (the C object is not thread-safe by design)"""
     _tls = threading.local()
@@ -106,7 +118,7 @@ class _PipeHandle:
     def get(cls, device_index: int, chunk_bytes: int) -> int:
         pipes = getattr(cls._tls, "pipes", None)
         if pipes is None:
-            pipes = cls._tls.pipes = {}
+            pipes = cls._tls.pipes = _ThreadPipes()
         key = (device_index, chunk_bytes)
         if key not in pipes:
             handle = C.c_void_p()

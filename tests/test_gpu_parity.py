@@ -618,3 +618,24 @@ def test_fp32_input_through_tma_kernel(native_lib, cuda_device, sym, g):
             if unpacked:
                 assert_same(q.cpu(), want["tensor_q"], what + "/tensor_q")
                 assert_same(zp.cpu(), want["zero_points"].reshape(C, G), what + "/zero_points")
+
+
+def test_quantize_model_from_worker_threads(native_lib, cuda_device):
+    """the CLI's --multi_gpu mode calls quantize_model from pool threads (main.py:596-621): every thread owns its pipe
+    (streams, device slots, pinned rings), which is destroyed when the thread ends"""
+    import gc
+    from concurrent.futures import ThreadPoolExecutor
+    tensors = {f"t{i}": datagen.weights((32 + 8 * i, 1024), "bf16", 500 + i) for i in range(6)}
+    want = {n: O.pack_result(O.group_quant_vec(t, 4, 128, False, True)) for n, t in tensors.items()}
+
+    def work(k):
+        qz = mk(symmetric=False)
+        out = qz.quantize_model(tensors, pack=True, chunk_bytes=1 << 16, keep_unpacked=bool(k & 1))
+        for n in tensors:
+            assert_quant_equal(out[n], want[n], f"{k}/{n}", keys=("scales", "qweight", "qzeros") + (("tensor_q",) if k & 1 else ()))
+        return k
+
+    for _ in range(2):                      # the second pool runs on fresh threads: fresh pipes, old ones released
+        with ThreadPoolExecutor(max_workers=4) as ex:
+            assert sorted(ex.map(work, range(8))) == list(range(8))
+        gc.collect()
