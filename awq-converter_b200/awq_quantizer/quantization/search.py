@@ -483,22 +483,6 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
     return out
 
 
-# ------------------------------------------------------------------------------------------------
-def smoke_check() -> None:
-    """tiny end-to-end search on cuda:0 against the oracle (called by __graft_entry__.smoke)"""
-    from oracle import awq_oracle as O
-    from tests import datagen
-    dev = torch.device("cuda", 0)
-    W = datagen.weights((256, 256), "bf16", 3)
-    X = datagen.activations(192, 256, "bf16", 4)
-    r = search_device(W.to(dev), X.to(dev), bits=4, group_size=128, symmetric=False, n_grid=4)
-    want = O.search_scales(W, X, 4, 128, False, n_grid=4, s_grid=r["s_grid"].cpu())
-    got = (r["err_sum"] / (192 * 256)).cpu()
-    for i in range(4):
-        assert abs(float(got[i]) - want["err"][i]) <= 1e-3 * want["err"][i], (i, float(got[i]), want["err"][i])
-    assert int(torch.argmin(got)) == want["best_idx"]
-
-
 def bench_leg(args, dev, world: int, rank: int, tf_peak: float, peak_kind: str):
     """bench.py's search leg: every linear of this rank's share of the workload, synthetic
     activations X[T, K] = N(0,1) * exp(N(0,1)) per channel, n_grid = 20.  Device-resident, CUDA-event

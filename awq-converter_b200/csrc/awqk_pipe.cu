@@ -383,6 +383,7 @@ extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* c
   std::vector<int64_t> voff((size_t)n_tensors + 1, 0);
   for (int i = 0; i < n_tensors; ++i) {
     if (src[i] == nullptr || numel[i] <= 0 || numel[i] % group_size != 0) return AWQK_E_BADARG;
+    if (zp_packed_host != nullptr && numel[i] % ((int64_t)group_size * per) != 0) return AWQK_E_BADARG;
     voff[i + 1] = voff[i] + (numel[i] + kTile - 1) / kTile * kTile;
   }
   const int64_t n = voff[n_tensors];

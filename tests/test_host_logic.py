@@ -103,3 +103,19 @@ def test_numa_binding_is_best_effort():
     assert parallel.bind_to_gpu_numa(0) in (None, 0, 1, 2, 3, 4, 5, 6, 7)        # never raises (no GPU here -> None)
     assert parallel.rank_info() == (0, 1, 0)
     assert parallel.gather_metadata({"rank": 0}) == [{"rank": 0}]
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under awq-converter_b200/ may import, load or execute it"""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "awq-converter_b200")
+    bad = []
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(d, f), errors="ignore").read()
+                # (comments may cite oracle/awq_oracle.py as the definition of the unpinned parts)
+                if re.search(r"^\s*(from|import)\s+oracle\b|libawq_oracle|import_module\(.oracle", text, flags=re.M):
+                    bad.append(os.path.relpath(os.path.join(d, f), root))
+    assert not bad, bad
