@@ -39,7 +39,7 @@ SIGNATURES = {
     "awqk_pipe_destroy": (None, [_vp]),
     "awqk_pipe_quant_host": (_int, [_vp, _vp, _int, _i64, _i64, _int, _int, _int, _int, _vp, _vp, _vp,
                                     _vp, _vp]),
-    "awqk_pipe_quant_gather": (_int, [_vp, _int, C.POINTER(_vp), C.POINTER(_i64), _int, _int, _int, _int, _int,
+    "awqk_pipe_quant_gather": (_int, [_vp, _int, C.POINTER(_vp), C.POINTER(_i64), _i64, _int, _int, _int, _int, _int,
                                       _vp, _vp, _vp, _vp, _vp]),
     "awqk_host_copy": (_int, [_vp, _vp, C.c_size_t, _int]),
     "awqk_pipe_sync": (_int, [_vp]),

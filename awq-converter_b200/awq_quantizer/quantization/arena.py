@@ -48,6 +48,21 @@ def arena_eligible(shape, dtype, group_size: int, bits: int) -> bool:
     return ((n // rows) // group_size) % (32 // bits) == 0
 
 
+def short_row_len(shape, dtype, group_size: int, bits: int) -> int:
+    """row length K of a tensor whose rows hold 1, 2 or 4 groups -- fewer than one packed zero word (K = 512 at
+    g = 128: OPT's embed_tokens / project_in) -- else 0.  Such tensors go through the gather pipeline in their
+    own class: K1 pads one zero word per row itself."""
+    if not pipe_eligible(shape, dtype, group_size, bits) or arena_eligible(shape, dtype, group_size, bits):
+        return 0
+    n = 1
+    for s in shape:
+        n *= s
+    rows = 1 if len(shape) <= 1 else shape[0]
+    k = n // rows
+    gr, per = k // group_size, 32 // bits
+    return k if (gr < per and per % gr == 0 and TILE % k == 0) else 0
+
+
 class HostArena:
     """Pinned host buffers (one per dtype) with a tile-aligned slot per tensor.
 
@@ -131,7 +146,7 @@ def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: b
                    device: torch.device, chunk_bytes: int = 32 << 20, want_zero_points: bool = False,
                    out: Optional[dict] = None, sync: bool = True, packed: bool = True,
                    unpacked: bool = False, sources: Optional[Dict[str, torch.Tensor]] = None,
-                   pin_results: bool = True) -> Dict[str, Dict[str, torch.Tensor]]:
+                   pin_results: bool = True, row_len: int = 0) -> Dict[str, Dict[str, torch.Tensor]]:
     """Quantize every tensor of ``arena`` through the chunked H2D -> K1 -> D2H pipeline.
 
     ``sources`` (name -> CPU tensor): the arena is virtual (``HostArena.for_tensors``); the native pipeline
@@ -139,6 +154,8 @@ def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: b
     the results into ordinary (pageable) host arrays -- no pinned allocation proportional to the model
     (cudaHostAlloc runs at ~2.3 GB/s, 20x slower than the pipeline itself), blocking.  With ``pin_results``
     the result arrays are pinned and written by the D2H copies directly (worth it when the allocation is re-used).
+    ``row_len`` (gather mode): all tensors have rows of this many elements = 1, 2 or 4 groups (``short_row_len``);
+    their ``qzeros`` are one zero-padded word per row.
 
     ``packed``   -> 'qweight' / 'qzeros' (+ 'scales'), ``unpacked`` -> the reference's 'tensor_q' int32 /
     'zero_points' int32 (+ 'scales').  The tensors are views of pinned host output arenas (``out`` may
@@ -153,12 +170,15 @@ def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: b
         buf = arena.buffers.get(dtype)
         n = arena.sizes[dtype]
         pin = torch.cuda.is_available() and (sources is None or pin_results)
-        key = (dtype, n, bits, group_size, want_z, packed, unpacked, pin)
+        if row_len and sources is None:
+            raise ValueError("row_len needs the gather mode (sources=...)")
+        n_zq = n // row_len if row_len else n // group_size // per
+        key = (dtype, n, bits, group_size, want_z, packed, unpacked, pin, row_len)
         if key not in outs:
             outs[key] = {
                 "q": torch.empty(n // per, dtype=torch.int32, pin_memory=pin) if packed else None,
                 "s": torch.empty(n // group_size, dtype=torch.float16, pin_memory=pin),
-                "zq": torch.empty(n // group_size // per, dtype=torch.int32, pin_memory=pin) if packed else None,
+                "zq": torch.empty(n_zq, dtype=torch.int32, pin_memory=pin) if packed else None,
                 "z": torch.empty(n // group_size, dtype=torch.int32, pin_memory=pin) if want_z else None,
                 "tq": torch.empty(n, dtype=torch.int32, pin_memory=pin) if unpacked else None,
             }
@@ -173,7 +193,7 @@ def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: b
             keep = [sources[name].detach().contiguous() for name, _, _ in lay]     # alive during the call
             ptrs = (C.c_void_p * len(lay))(*[t.data_ptr() for t in keep])
             nums = (C.c_int64 * len(lay))(*[numel for _, _, numel in lay])
-            N.check(L.awqk_pipe_quant_gather(pipe, len(lay), ptrs, nums, N.dtype_code(dtype), group_size, bits,
+            N.check(L.awqk_pipe_quant_gather(pipe, len(lay), ptrs, nums, row_len, N.dtype_code(dtype), group_size, bits,
                                              int(symmetric), ar, N.ptr(o["tq"]), N.ptr(o["q"]), o["s"].data_ptr(),
                                              N.ptr(o["z"]), N.ptr(o["zq"])), "awqk_pipe_quant_gather")
             del keep
@@ -193,7 +213,10 @@ def quantize_arena(arena: HostArena, *, bits: int, group_size: int, symmetric: b
             r["symmetric"] = torch.tensor(symmetric, dtype=torch.bool)
             if packed:
                 r["qweight"] = o["q"][off // per:(off + numel) // per].view(rows, k // per)
-                r["qzeros"] = o["zq"][off // group_size // per:(off + numel) // group_size // per].view(rows, g // per)
+                if row_len:
+                    r["qzeros"] = o["zq"][off // row_len:(off + numel) // row_len].view(rows, 1)
+                else:
+                    r["qzeros"] = o["zq"][off // group_size // per:(off + numel) // group_size // per].view(rows, g // per)
             results[name] = r
     if sync:
         N.check(L.awqk_pipe_sync(pipe), "awqk_pipe_sync")

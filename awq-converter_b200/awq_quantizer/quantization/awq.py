@@ -279,7 +279,7 @@ class AWQQuantizer:
             return {n: quantized[n] for n in tensors if n in quantized}       # input order, like the reference
 
         from .arena import (HostArena, arena_eligible, pipe_eligible, quantize_arena, quantize_rows_pipelined,
-                            sync_pipe)
+                            short_row_len, sync_pipe)
         dev = self._cuda_device()
         self._check_zero_point_mode()
         quantized = {}
@@ -304,6 +304,18 @@ class AWQQuantizer:
                                             chunk_bytes=chunk_bytes, sync=False, unpacked=keep, want_zero_points=keep,
                                             sources=None if isinstance(tensors, HostArena) else flat,
                                             pin_results=isinstance(tensors, HostArena) or pin))
+        # rows of 1 / 2 / 4 groups (K = 512 at g = 128): gather pipeline too, one class per row length
+        short: Dict[int, Dict[str, torch.Tensor]] = {}
+        for name, tensor in list(singles.items()):
+            if isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu":
+                k = short_row_len(tuple(tensor.shape), tensor.dtype, self.group_size, self.bits)
+                if k:
+                    short.setdefault(k, {})[name] = singles.pop(name)
+        for k, group in short.items():
+            quantized.update(quantize_arena(HostArena.for_tensors(group), bits=self.bits, group_size=self.group_size,
+                                            symmetric=self.symmetric, arith=self.arith, device=dev,
+                                            chunk_bytes=chunk_bytes, sync=False, unpacked=keep, want_zero_points=keep,
+                                            sources=group, pin_results=pin, row_len=k))
         rest = {}
         for name, tensor in singles.items():           # rows of whole groups: same pipeline, chunked by rows
             if not keep and isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu" and \

@@ -369,7 +369,7 @@ extern "C" int awqk_host_copy(void* dst, const void* src, size_t bytes, int thre
 }
 
 extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* const* src, const int64_t* numel,
-                                      int dtype, int group_size, int bits, int symmetric, int arith,
+                                      int64_t row_len, int dtype, int group_size, int bits, int symmetric, int arith,
                                       int32_t* q_unpacked_host, uint32_t* q_packed_host, void* scales_f16_host,
                                       int32_t* zp_host, uint32_t* zp_packed_host) {
   if (p == nullptr || src == nullptr || numel == nullptr || scales_f16_host == nullptr || n_tensors <= 0)
@@ -381,9 +381,15 @@ extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* c
   const size_t esz = (dtype == AWQK_FP32) ? 4 : 2;
   constexpr int64_t kTile = 8192;
   std::vector<int64_t> voff((size_t)n_tensors + 1, 0);
+  if (row_len != 0) {
+    // short rows (fewer groups than a packed zero word holds): K1 pads one zero word per row itself
+    const int64_t gr = row_len / group_size;
+    if (row_len < 0 || row_len % group_size != 0 || gr >= per || per % gr != 0 || kTile % row_len != 0) return AWQK_E_BADARG;
+  }
   for (int i = 0; i < n_tensors; ++i) {
     if (src[i] == nullptr || numel[i] <= 0 || numel[i] % group_size != 0) return AWQK_E_BADARG;
-    if (zp_packed_host != nullptr && numel[i] % ((int64_t)group_size * per) != 0) return AWQK_E_BADARG;
+    if (row_len != 0 && numel[i] % row_len != 0) return AWQK_E_BADARG;
+    if (row_len == 0 && zp_packed_host != nullptr && numel[i] % ((int64_t)group_size * per) != 0) return AWQK_E_BADARG;
     voff[i + 1] = voff[i] + (numel[i] + kTile - 1) / kTile * kTile;
   }
   const int64_t n = voff[n_tensors];
@@ -428,6 +434,9 @@ extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* c
 
   const int threads = pipe_threads();
   const int64_t n_chunks = (n + chunk_elems - 1) / chunk_elems;
+  // packed zero words: flat = one per `per` groups; short rows = one per row
+  auto zq_off = [=](int64_t e) { return row_len ? e / row_len : e / group_size / per; };
+  auto zq_words = [=](int64_t ne_) { return row_len ? ne_ / row_len : (ne_ / group_size + per - 1) / per; };
   // ---- drain thread: chunk c is copied out once its D2H event fired; then its output slot is free ----
   std::mutex mu;
   std::condition_variable cv;
@@ -457,7 +466,7 @@ extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* c
       if (q_unpacked_host) parallel_copy(q_unpacked_host + e0, o + lay.qu, (size_t)ne * 4, threads);
       memcpy(static_cast<uint16_t*>(scales_f16_host) + e0 / group_size, o + lay.sc, (size_t)ng * 2);
       if (zp_host) memcpy(zp_host + e0 / group_size, o + lay.zp, (size_t)ng * 4);
-      if (zp_packed_host) memcpy(zp_packed_host + e0 / group_size / per, o + lay.zq, (size_t)((ng + per - 1) / per) * 4);
+      if (zp_packed_host) memcpy(zp_packed_host + zq_off(e0), o + lay.zq, (size_t)zq_words(ne) * 4);
       {
         std::lock_guard<std::mutex> lk(mu);
         drained = c + 1;
@@ -512,10 +521,10 @@ extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* c
     AWQK_CUDA_G(cudaEventRecord(p->ev_h2d[b], p->s_in));
     AWQK_CUDA_G(cudaStreamWaitEvent(p->s_k, p->ev_h2d[b], 0));
     if (c >= kBuf) AWQK_CUDA_G(cudaStreamWaitEvent(p->s_k, p->ev_out[b], 0));   // device output slot drained to the host
-    const int rc = awqk_group_quant(p->d_in[b], dtype, 1, ne, group_size, bits, symmetric, arith,
-                                    q_unpacked_host ? p->d_qu[b] : nullptr, q_packed_host ? p->d_qp[b] : nullptr,
-                                    p->d_sc[b], zp_host ? p->d_zp[b] : nullptr, zp_packed_host ? p->d_zpp[b] : nullptr,
-                                    nullptr, p->s_k);
+    const int rc = awqk_group_quant(p->d_in[b], dtype, row_len ? ne / row_len : 1, row_len ? row_len : ne, group_size, bits,
+                                    symmetric, arith, q_unpacked_host ? p->d_qu[b] : nullptr,
+                                    q_packed_host ? p->d_qp[b] : nullptr, p->d_sc[b], zp_host ? p->d_zp[b] : nullptr,
+                                    zp_packed_host ? p->d_zpp[b] : nullptr, nullptr, p->s_k);
     if (rc != AWQK_OK) return finish(rc);
     AWQK_CUDA_G(cudaEventRecord(p->ev_k[b], p->s_k));
     AWQK_CUDA_G(cudaStreamWaitEvent(p->s_out, p->ev_k[b], 0));
@@ -524,7 +533,7 @@ extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* c
     void* dst_qu = direct ? static_cast<void*>(q_unpacked_host + e0) : o + lay.qu;
     void* dst_sc = direct ? static_cast<void*>(static_cast<uint16_t*>(scales_f16_host) + e0 / group_size) : o + lay.sc;
     void* dst_zp = direct ? static_cast<void*>(zp_host + e0 / group_size) : o + lay.zp;
-    void* dst_zq = direct ? static_cast<void*>(zp_packed_host + e0 / group_size / per) : o + lay.zq;
+    void* dst_zq = direct ? static_cast<void*>(zp_packed_host + zq_off(e0)) : o + lay.zq;
     if (q_packed_host)
       AWQK_CUDA_G(cudaMemcpyAsync(dst_qp, p->d_qp[b], (size_t)(ne / per) * 4, cudaMemcpyDeviceToHost, p->s_out));
     if (q_unpacked_host)
@@ -532,7 +541,7 @@ extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* c
     AWQK_CUDA_G(cudaMemcpyAsync(dst_sc, p->d_sc[b], (size_t)ng * 2, cudaMemcpyDeviceToHost, p->s_out));
     if (zp_host) AWQK_CUDA_G(cudaMemcpyAsync(dst_zp, p->d_zp[b], (size_t)ng * 4, cudaMemcpyDeviceToHost, p->s_out));
     if (zp_packed_host)
-      AWQK_CUDA_G(cudaMemcpyAsync(dst_zq, p->d_zpp[b], (size_t)((ng + per - 1) / per) * 4, cudaMemcpyDeviceToHost, p->s_out));
+      AWQK_CUDA_G(cudaMemcpyAsync(dst_zq, p->d_zpp[b], (size_t)zq_words(ne) * 4, cudaMemcpyDeviceToHost, p->s_out));
     AWQK_CUDA_G(cudaEventRecord(p->ev_out[b], p->s_out));
     p->used[b] = true;
     {

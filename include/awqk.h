@@ -162,10 +162,12 @@ AWQK_API int awqk_pipe_quant_host(awqk_pipe* p, const void* w_host, int dtype, i
  * threads, default by core count) and a drain thread copies finished chunks into the result arrays, which are
  * flat over the virtual arena exactly as in awqk_pipe_quant_host (C = 1, K = v_n).  Every numel[i] must be a
  * multiple of group_size (of group_size * 32 / bits when zp_packed_host is given, so that packed zero words
- * never straddle tensors).  BLOCKING: returns when all results are in place.  Replaces the reference's
+ * never straddle tensors).  row_len = 0: that flat layout.  row_len > 0: every tensor is made of rows of row_len
+ * elements holding 1, 2 or 4 groups (fewer than a packed zero word): zp_packed gets ONE zero-padded word per row
+ * (K = 512 at g = 128, e.g. OPT's embed_tokens / project_in).  BLOCKING: returns when all results are in place.  Replaces the reference's
  * per-tensor tensor.to(device) / .cpu() round trips (main.py:300, 374-380) for a whole model. */
 AWQK_API int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* const* src, const int64_t* numel,
-                           int dtype, int group_size, int bits, int symmetric, int arith,
+                           int64_t row_len, int dtype, int group_size, int bits, int symmetric, int arith,
                            int32_t* q_unpacked_host, uint32_t* q_packed_host, void* scales_f16_host,
                            int32_t* zp_host, uint32_t* zp_packed_host);
 /* memcpy split over `threads` host threads (0 = the pipe's default: AWQK_PIPE_THREADS or by core count).  One

@@ -510,12 +510,15 @@ def test_gather_c_abi_errors(native_lib, cuda_device):
     try:
         ptrs = (C.c_void_p * 1)(w.data_ptr())
         nums = (C.c_int64 * 1)(4000)
-        args = (N.BF16, 128, 4, 0, N.ARITH_NATIVE, None, None, sc.data_ptr(), None, None)
+        args = (0, N.BF16, 128, 4, 0, N.ARITH_NATIVE, None, None, sc.data_ptr(), None, None)
         assert native_lib.awqk_pipe_quant_gather(h, 1, ptrs, nums, *args) == -1
         nums[0] = 0
         assert native_lib.awqk_pipe_quant_gather(h, 1, ptrs, nums, *args) == -1
         assert native_lib.awqk_pipe_quant_gather(h, 0, ptrs, nums, *args) == -1
         assert native_lib.awqk_pipe_quant_gather(None, 1, ptrs, nums, *args) == -1
+        nums[0] = 3840                                          # rows of 384 = 3 groups: not a short-row class
+        assert native_lib.awqk_pipe_quant_gather(h, 1, ptrs, nums, 384, *args[1:]) == -1
+        assert native_lib.awqk_pipe_quant_gather(h, 1, ptrs, nums, 1024, *args[1:]) == -1     # 8 groups = a whole word
     finally:
         native_lib.awqk_pipe_destroy(h)
 
@@ -639,3 +642,19 @@ def test_quantize_model_from_worker_threads(native_lib, cuda_device):
         with ThreadPoolExecutor(max_workers=4) as ex:
             assert sorted(ex.map(work, range(8))) == list(range(8))
         gc.collect()
+
+
+@pytest.mark.parametrize("keep", [False, True])
+def test_short_row_tensors_through_gather(native_lib, cuda_device, keep):
+    """rows of 1 / 2 / 4 groups (OPT's K = 512 tensors) join the gather pipeline in a class of their own: qzeros is one
+    zero-padded word per row, written by K1"""
+    tensors = {"embed": datagen.weights((300, 512), "bf16", 1), "proj": datagen.weights((64, 512), "bf16", 2),
+               "k256": datagen.weights((40, 256), "bf16", 3), "k128": datagen.weights((9, 128), "fp16", 4),
+               "full": datagen.weights((16, 1024), "bf16", 5), "odd": datagen.weights((8, 1536), "bf16", 6)}
+    for sym in (False, True):
+        out = mk(symmetric=sym).quantize_model(tensors, pack=True, chunk_bytes=1 << 16, keep_unpacked=keep)
+        assert list(out) != [] and sorted(out) == sorted(tensors)
+        for n, t in tensors.items():
+            want = O.pack_result(O.group_quant_vec(t, 4, 128, sym, True))
+            keys = ("scales", "qweight", "qzeros") + (("tensor_q", "zero_points") if keep else ())
+            assert_quant_equal(out[n], want, f"{n}/{sym}", keys=keys)
