@@ -307,7 +307,8 @@ class AWQQuantizer:
         # rows of 1 / 2 / 4 groups (K = 512 at g = 128): gather pipeline too, one class per row length
         short: Dict[int, Dict[str, torch.Tensor]] = {}
         for name, tensor in list(singles.items()):
-            if isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu":
+            # (a tensor that is already pinned takes the zero-copy, asynchronous row pipeline below)
+            if isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu" and not tensor.is_pinned():
                 k = short_row_len(tuple(tensor.shape), tensor.dtype, self.group_size, self.bits)
                 if k:
                     short.setdefault(k, {})[name] = singles.pop(name)
