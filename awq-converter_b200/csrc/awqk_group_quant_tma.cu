@@ -591,7 +591,10 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     }
     if (has_zq) {
       const uint32_t uz = (valid && leader && zi != INT32_MIN) ? ((uint32_t)(zi - QMIN) & CMAX) : 0u;
-      const uint32_t wordz = __reduce_or_sync(zq_mask, uz << zq_shift);
+      // (a compile-time full mask lets the compiler drop the re-convergence sequence around REDUX: the common
+      // g = 128 / int4 case packs one word per warp)
+      const uint32_t wordz = (LPW == 32) ? __reduce_or_sync(0xFFFFFFFFu, uz << zq_shift)
+                                         : __reduce_or_sync(zq_mask, uz << zq_shift);
       if (valid && zq_writer) *reinterpret_cast<uint32_t*>(zq_base + (uint64_t)it * zq_step) = wordz;
     }
   }
