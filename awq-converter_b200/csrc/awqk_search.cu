@@ -131,6 +131,16 @@ __device__ __forceinline__ float dq_fmin_nan(float a, float b) {
   asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
+__device__ __forceinline__ float dq_fmin3_nan(float a, float b, float c) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ float dq_fmax3_nan(float a, float b, float c) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ float dq_fmax_nan(float a, float b) {
   float r;
   asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
@@ -470,9 +480,9 @@ fakequant_delta_v4(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
     for (int i = 0; i < 8; ++i) x[i] = __fmul2_rn(wv[i], sv[i]);                   // Ws = W * s
     float mn = dq_fmin_nan(x[0].x, x[0].y), mx = dq_fmax_nan(x[0].x, x[0].y);
 #pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      mn = dq_fmin_nan(mn, dq_fmin_nan(x[i].x, x[i].y));
-      mx = dq_fmax_nan(mx, dq_fmax_nan(x[i].x, x[i].y));
+    for (int i = 1; i < 8; ++i) {                                  // 3-input FMNMX: one instruction per pair
+      mn = dq_fmin3_nan(mn, x[i].x, x[i].y);
+      mx = dq_fmax3_nan(mx, x[i].x, x[i].y);
     }
 #pragma unroll
     for (int m = 1; m < LPG; m <<= 1) {
@@ -483,7 +493,10 @@ fakequant_delta_v4(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
     uint32_t o[8];
     if (fg.ok) {
       const float2 r2 = make_float2(fg.rcp, fg.rcp), ns2 = make_float2(-fg.scale, -fg.scale);
-      const float2 zp2 = make_float2(fg.zp, fg.zp), nzp2 = make_float2(-fg.zp, -fg.zp);
+      // rint(v) - zp = (v + M) - (M + zp): M + zp is an exact integer below 2^24, the difference of two such
+      // integers is exact -- one packed add instead of two
+      const float2 zp2 = make_float2(fg.zp, fg.zp);
+      const float2 nmz2 = make_float2(-(12582912.0f + fg.zp), -(12582912.0f + fg.zp));
       const float2 sc2 = make_float2(fg.scale, fg.scale);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -494,8 +507,7 @@ fakequant_delta_v4(const T* __restrict__ w, int64_t C, int64_t K, bool sym, cons
         float2 v = __fadd2_rn(q, zp2);
         v.x = fminf(fmaxf(v.x, qmin), qmax);
         v.y = fminf(fmaxf(v.y, qmin), qmax);
-        const float2 qf = __fadd2_rn(__fadd2_rn(v, magic2), nmagic2);              // rint (half-to-even)
-        const float2 d = __fmul2_rn(__fadd2_rn(qf, nzp2), sc2);                    // (q - zp) * scale
+        const float2 d = __fmul2_rn(__fadd2_rn(__fadd2_rn(v, magic2), nmz2), sc2); // (rint(v) - zp) * scale
         const float2 h0 = __fmul2_rn(d, rs);
         const float2 nsv = make_float2(-sv[i].x, -sv[i].y);
         const float2 what = __ffma2_rn(__ffma2_rn(nsv, h0, d), rs, h0);            // deq / s, exact
