@@ -119,3 +119,27 @@ def test_product_package_never_touches_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|libawq_oracle|import_module\(.oracle", text, flags=re.M):
                     bad.append(os.path.relpath(os.path.join(d, f), root))
     assert not bad, bad
+
+
+def test_arena_layout_and_short_row_classes():
+    """host-side layout rules of the pipelines (no device): tile-aligned virtual arena, eligibility classes"""
+    from awq_quantizer.quantization.arena import TILE, HostArena, arena_eligible, pipe_eligible, short_row_len
+    bf, f32 = torch.bfloat16, torch.float32
+    assert arena_eligible((4096, 1024), bf, 128, 4) and arena_eligible((1024,), bf, 128, 4)
+    assert not arena_eligible((1024, 512), bf, 128, 4) and pipe_eligible((1024, 512), bf, 128, 4)     # 4 groups per row
+    assert not pipe_eligible((7, 300), bf, 128, 4) and not pipe_eligible((10, 10), bf, 128, 4)
+    assert not pipe_eligible((8, 1024), torch.float64, 128, 4) and not pipe_eligible((8, 1024), bf, 96, 4)
+    assert short_row_len((1024, 512), bf, 128, 4) == 512 and short_row_len((9, 128), bf, 128, 4) == 128
+    assert short_row_len((40, 256), f32, 128, 4) == 256 and short_row_len((8, 64), bf, 32, 4) == 64
+    assert short_row_len((8, 1536), bf, 128, 4) == 0            # 12 groups: neither a whole word nor a short row
+    assert short_row_len((8, 384), bf, 128, 4) == 0             # 3 groups do not divide a word
+    assert short_row_len((8, 1024), bf, 128, 4) == 0            # whole words: the flat class
+    assert short_row_len((8, 512), bf, 128, 8) == 0 and short_row_len((8, 256), bf, 128, 8) == 256    # int8: 4 per word
+    tensors = {"a": torch.zeros(3, 1024, dtype=bf), "b": torch.zeros(1024, dtype=bf), "h": torch.zeros(5, 2048, dtype=torch.float16)}
+    arena = HostArena.for_tensors(tensors)
+    assert not arena.buffers and arena.sizes == {bf: 2 * TILE, torch.float16: 2 * TILE}
+    assert arena.layout[bf] == [("a", 0, 3072), ("b", TILE, 1024)] and arena.layout[torch.float16] == [("h", 0, 10240)]
+    real = HostArena.from_tensors({k: v + 1 for k, v in tensors.items()}, pin=False)
+    assert real.views["b"].shape == (1024,) and float(real.buffers[bf][TILE]) == 1.0
+    assert float(real.buffers[bf][3072]) == 0.0 and float(real.buffers[bf][TILE - 1]) == 0.0          # padding is zeroed
+    assert real.payload_bytes() == (3072 + 1024 + 10240) * 2
