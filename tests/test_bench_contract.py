@@ -1,0 +1,44 @@
+"""bench.py's reference arm runs on host cores only, so its side of the contract is checked here without a GPU:
+exactly one JSON line on stdout, the keys the driver reads, rank 0 alone working under torchrun."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+        "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches")
+
+
+def _check(stdout: str, n_gpus: int):
+    lines = [l for l in stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in KEYS:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["n_gpus"] == n_gpus and d["steps"] == 1 and d["gpu_launches"] == 0
+    assert d["metric"].startswith("quantize+pack GB/s of BF16 weights") and d["unit"] == "GB/s" and d["value"] > 0
+    assert d["vs_baseline"] is None and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_single_process():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    _check(out.stdout, 1)
+
+
+@pytest.mark.timeout(900)
+def test_reference_arm_under_torchrun_two_ranks():
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=800, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    _check(out.stdout, 2)
