@@ -221,266 +221,8 @@ class SearchPipeline:
         return out
 
 
-def _align(n: int, a: int = 256) -> int:
-    return (n + a - 1) // a * a
-
-
-class _PinnedArena:
-    """one pinned host allocation per (wave, dtype), carved into per-tensor views (a cudaHostAlloc per
-    result tensor would cost more than the transfers)"""
-
-    def __init__(self):
-        self.want = {}                     # dtype -> bytes
-        self.slots = []                    # (key, dtype, shape, offset)
-
-    def add(self, key, dtype: torch.dtype, shape) -> None:
-        n = 1
-        for d in shape:
-            n *= d
-        off = self.want.get(dtype, 0)
-        self.slots.append((key, dtype, tuple(shape), off))
-        self.want[dtype] = off + _align(n * torch.empty((), dtype=dtype).element_size())
-
-    def allocate(self) -> dict:
-        bufs = {dt: torch.empty(nb, dtype=torch.uint8, pin_memory=True) for dt, nb in self.want.items()}
-        out = {}
-        for key, dt, shape, off in self.slots:
-            n = 1
-            for d in shape:
-                n *= d
-            nb = n * torch.empty((), dtype=dt).element_size()
-            out[key] = bufs[dt][off:off + nb].view(dt).view(shape)
-        return out
-
-
-def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations: Dict[str, torch.Tensor],
-                               dev: torch.device, *, pack: bool = False, keep_unpacked: Optional[bool] = None,
-                               wave_bytes: int = 256 << 20, pin_results: bool = False) -> Dict[str, Dict[str, torch.Tensor]]:
-    """Model-level AWQ from host tensors, streamed: every 2-D tensor that has calibration activations goes
-    through the search pipeline (SearchPipeline) and the final K1 pass on W * s_best.
-
-    The model is cut into waves of ``wave_bytes``.  An uploader thread stages wave i+1 into pinned memory
-    and copies it to the device (copy stream) while wave i is searched and quantized (compute streams) and
-    the results of wave i-1 drain to the host (output stream): two device slots, two pinned staging slots,
-    CUDA events between the streams, one host synchronisation at the end.  Results land in a ring of three
-    pinned slots and a drain thread copies them into ordinary tensors (no pinned allocation proportional to
-    the model); with ``pin_results`` they are written straight into per-wave pinned arenas instead (worth
-    it when the pinned blocks are re-used by later models).
-
-    Results carry the reference's keys plus ``awq_scale`` / ``alpha`` / ``best_idx`` / ``search_err``
-    (+ ``qweight`` / ``qzeros`` with pack).  ``tensor_q`` (4 bytes per element over PCIe) is produced when
-    ``keep_unpacked`` -- default: only without ``pack``, like the packed path of ``quantize_model``."""
-    import queue
-    import threading
-    keep_unpacked = (not pack) if keep_unpacked is None else (keep_unpacked or not pack)
-    names = [n for n, t in tensors.items() if n in activations]
-    for n in names:
-        _check(tensors[n], activations[n], qz.group_size)
-    if not names:
-        return {}
-    per = 32 // qz.bits
-    g = qz.group_size
-
-    # ---- waves ------------------------------------------------------------------------------------
-    def nbytes(t):
-        return _align(t.numel() * t.element_size())
-    waves, cur_wave, cur_b = [], [], 0
-    for n in names:
-        b = nbytes(tensors[n])
-        if cur_wave and cur_b + b > wave_bytes:
-            waves.append(cur_wave)
-            cur_wave, cur_b = [], 0
-        cur_wave.append(n)
-        cur_b += b
-    waves.append(cur_wave)
-    host_waves = [[n for n in w if tensors[n].device.type != "cuda"] for w in waves]
-    slot_bytes = max([sum(nbytes(tensors[n]) for n in w) for w in host_waves] + [256])
-    n_slots = min(2, len(waves))
-    d_slot = [torch.empty(slot_bytes, dtype=torch.uint8, device=dev) for _ in range(n_slots)]
-    need_stage = any(not tensors[n].is_pinned() for w in host_waves for n in w)
-    h_slot = [torch.empty(slot_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(n_slots)] if need_stage else []
-
-    cur = torch.cuda.current_stream(dev)
-    s_copy, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    s_copy.wait_stream(cur)
-    ready: "queue.Queue" = queue.Queue()
-    compute_done = [None] * len(waves)                 # CUDA events, recorded by the main thread
-    compute_rec = [threading.Event() for _ in waves]   # ... and the host-side notice that they exist
-    abort = threading.Event()
-
-    def uploader():
-        try:
-            torch.cuda.set_device(dev)
-            h2d_done = []
-            for wi, wave in enumerate(waves):
-                slot = wi % n_slots
-                if wi >= n_slots:
-                    h2d_done[wi - n_slots].synchronize()            # pinned staging slot is free again
-                    while not compute_rec[wi - n_slots].wait(0.05):  # device slot: wait for the event to exist
-                        if abort.is_set():
-                            return
-                    s_copy.wait_event(compute_done[wi - n_slots])
-                views, off = {}, 0
-                for n in wave:
-                    t = tensors[n]
-                    if t.device.type == "cuda":
-                        views[n] = t.to(dev).contiguous()
-                        continue
-                    nb = t.numel() * t.element_size()
-                    dv = d_slot[slot][off:off + nb].view(t.dtype).view(t.shape)
-                    src = t.detach()
-                    if not src.is_pinned():
-                        hv = h_slot[slot][off:off + nb].view(t.dtype).view(t.shape)
-                        N.host_copy(hv, src)
-                        src = hv
-                    with torch.cuda.stream(s_copy):
-                        dv.copy_(src, non_blocking=True)
-                    views[n] = dv
-                    off += _align(nb)
-                ev = torch.cuda.Event()
-                ev.record(s_copy)
-                h2d_done.append(ev)
-                ready.put((views, ev))
-        except BaseException as e:      # surfaces in the main thread
-            ready.put(e)
-
-    th = threading.Thread(target=uploader, name="awq-upload", daemon=True)
-    th.start()
-
-    x_dev: Dict[int, torch.Tensor] = {}
-    pipe = SearchPipeline(dev, bits=qz.bits, group_size=g, symmetric=qz.symmetric, n_grid=qz.n_grid)
-    host_out: Dict[str, Dict[str, torch.Tensor]] = {}
-    inflight = []                                       # (device tensors kept alive, D2H-done event)
-
-    # ---- result ring + drain thread (pageable results) ---------------------------------------------
-    def out_bytes(t):
-        C, K = t.shape
-        G = K // g
-        b = _align(C * G * 2) + _align(C * G * 4) + _align(qz.n_grid * 8) + _align(4) + _align(K * 4)
-        if pack:
-            b += _align(C * (-(-K // per)) * 4) + _align(C * (-(-G // per)) * 4)
-        if keep_unpacked:
-            b += _align(C * K * 4)
-        return b
-    n_out_slots = 3
-    ring = []
-    if not pin_results:
-        out_slot_bytes = max(sum(out_bytes(tensors[n]) for n in w) for w in waves)
-        ring = [torch.empty(out_slot_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(min(n_out_slots, len(waves)))]
-    out_q: "queue.Queue" = queue.Queue()
-    slot_free = threading.Semaphore(max(1, len(ring)))
-    drain_err = []
-
-    def drainer():
-        try:
-            torch.cuda.set_device(dev)
-            while True:
-                item = out_q.get()
-                if item is None:
-                    return
-                slot, entries, ev, keep = item
-                ev.synchronize()
-                for name, k, off, nb, dt, shape in entries:
-                    final = torch.empty(shape, dtype=dt)
-                    N.host_copy(final, ring[slot][off:off + nb].view(dt).view(shape))
-                    host_out.setdefault(name, {})[k] = final
-                del keep, item
-                slot_free.release()
-        except BaseException as e:
-            drain_err.append(e)
-            slot_free.release()
-
-    dth = threading.Thread(target=drainer, name="awq-drain", daemon=True)
-    dth.start()
-    try:
-        for wi, wave in enumerate(waves):
-            item = ready.get()
-            if isinstance(item, BaseException):
-                raise item
-            views, ev = item
-            cur.wait_event(ev)
-            for n in wave:
-                x = activations[n]
-                if id(x) not in x_dev:
-                    x_dev[id(x)] = x.to(dev, non_blocking=True).contiguous()
-                pipe.submit(n, views[n], x_dev[id(x)])
-            res = pipe.finish()
-            dev_out = {}
-            for name, mean, best, s_best in res:
-                s_best = s_best.contiguous()
-                o = qz._quantize_device(views[name], pack=pack, unpacked=keep_unpacked, col_scale=s_best, arith="fp32")
-                o.update({"search_err": mean, "best_idx": best.to(torch.int32), "awq_scale": s_best})
-                dev_out[name] = {k: v for k, v in o.items() if v is not None}
-            cd = torch.cuda.Event()
-            cd.record(cur)
-            compute_done[wi] = cd
-            compute_rec[wi].set()
-            if not pin_results:
-                # results -> pinned ring slot on the output stream -> drain thread -> ordinary tensors
-                slot_free.acquire()
-                if drain_err:
-                    raise drain_err[0]
-                slot = wi % len(ring)
-                entries, off = [], 0
-                s_out.wait_event(cd)
-                with torch.cuda.stream(s_out):
-                    for name, o in dev_out.items():
-                        for k, v in o.items():
-                            nb = v.numel() * v.element_size()
-                            ring[slot][off:off + nb].view(v.dtype).view(v.shape).copy_(v, non_blocking=True)
-                            entries.append((name, k, off, nb, v.dtype, tuple(v.shape)))
-                            off += _align(nb)
-                od = torch.cuda.Event()
-                od.record(s_out)
-                out_q.put((slot, entries, od, (dev_out, views)))
-                continue
-            # results -> pinned arenas on the output stream
-            arena = _PinnedArena()
-            for name, o in dev_out.items():
-                for k, v in o.items():
-                    arena.add((name, k), v.dtype, v.shape)
-            hviews = arena.allocate()
-            s_out.wait_event(cd)
-            with torch.cuda.stream(s_out):
-                for (name, k), hv in hviews.items():
-                    hv.copy_(dev_out[name][k], non_blocking=True)
-            od = torch.cuda.Event()
-            od.record(s_out)
-            inflight.append((dev_out, views, od))
-            if len(inflight) > 2:                        # bound the device memory held by finished waves
-                inflight[0][2].synchronize()
-                inflight.pop(0)
-            for (name, k), hv in hviews.items():
-                host_out.setdefault(name, {})[k] = hv
-        out_q.put(None)
-        dth.join()
-        if drain_err:
-            raise drain_err[0]
-        s_out.synchronize()
-        cur.wait_stream(s_out)
-    except BaseException:
-        abort.set()
-        out_q.put(None)
-        raise
-    finally:
-        th.join(timeout=60)
-        dth.join(timeout=60)
-    out: Dict[str, Dict[str, torch.Tensor]] = {}
-    for name in names:
-        host = host_out[name]
-        b = int(host["best_idx"])
-        r = {"tensor_q": host.get("tensor_q"), "scales": host["scales"], "zero_points": host["zero_points"],
-             "bits": torch.tensor(qz.bits, dtype=torch.int32),
-             "group_size": torch.tensor(qz.group_size, dtype=torch.int32),
-             "symmetric": torch.tensor(qz.symmetric, dtype=torch.bool),
-             "awq_scale": host["awq_scale"], "alpha": torch.tensor(b / qz.n_grid, dtype=torch.float32),
-             "best_idx": host["best_idx"], "search_err": host["search_err"]}
-        if r["tensor_q"] is None:
-            del r["tensor_q"]
-        if pack:
-            r["qweight"], r["qzeros"] = host["qweight"], host["qzeros"]
-        out[name] = r
-    return out
+# model-level, streamed form (uploader thread / search / result ring): quantization/stream.py
+from .stream import quantize_model_with_search  # noqa: E402,F401  (re-exported: the public entry of this module)
 
 
 def bench_leg(args, dev, world: int, rank: int, tf_peak: float, peak_kind: str):

@@ -1,0 +1,290 @@
+"""Model-level AWQ from host tensors, streamed in waves (the end-to-end path of
+``AWQQuantizer.quantize_model(tensors, activations=...)``).
+
+    uploader thread   wave i+1: pageable tensor -> pinned staging slot (native parallel copy) -> device slot (copy stream)
+    caller's thread   wave i  : SearchPipeline (delta + tcgen05 GEMM streams) -> argmin -> K1 on W * s_best
+    output stream     wave i-1: results -> pinned ring slot -> drain thread -> ordinary host tensors
+
+Two device slots and two pinned staging slots for the weights, three pinned ring slots for the results, CUDA
+events between the streams, one host synchronisation at the end.  No pinned allocation proportional to the model
+(cudaHostAlloc runs at ~2.3 GB/s, 20x slower than this pipeline).  Replaces the reference's per-tensor
+``tensor.to(device)`` ... ``.cpu()`` round trips (awq.py:402, 410-412; main.py:353-392) for the searched tensors.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import _native as N
+
+
+def _align(n: int, a: int = 256) -> int:
+    return (n + a - 1) // a * a
+
+
+def _nbytes(t: torch.Tensor) -> int:
+    return t.numel() * t.element_size()
+
+
+def plan_waves(names: List[str], tensors: Dict[str, torch.Tensor], wave_bytes: int) -> List[List[str]]:
+    """input order, greedily filled up to ``wave_bytes`` (a larger tensor is a wave of its own)"""
+    waves, cur, cur_b = [], [], 0
+    for n in names:
+        b = _align(_nbytes(tensors[n]))
+        if cur and cur_b + b > wave_bytes:
+            waves.append(cur)
+            cur, cur_b = [], 0
+        cur.append(n)
+        cur_b += b
+    if cur:
+        waves.append(cur)
+    return waves
+
+
+class WaveUploader(threading.Thread):
+    """Stages the waves into device memory ahead of the consumer.
+
+    ``ready`` yields ``(views, event)`` per wave in order (or an exception).  The consumer must call
+    ``release(wi, event)`` with an event recorded after its last read of wave ``wi``: only then is the wave's
+    device slot overwritten."""
+
+    def __init__(self, dev: torch.device, tensors: Dict[str, torch.Tensor], waves: List[List[str]]):
+        super().__init__(name="awq-upload", daemon=True)
+        self.dev, self.tensors, self.waves = dev, tensors, waves
+        host_waves = [[n for n in w if tensors[n].device.type != "cuda"] for w in waves]
+        slot_bytes = max([sum(_align(_nbytes(tensors[n])) for n in w) for w in host_waves] + [256])
+        self.n_slots = min(2, len(waves))
+        self.d_slot = [torch.empty(slot_bytes, dtype=torch.uint8, device=dev) for _ in range(self.n_slots)]
+        need_stage = any(not tensors[n].is_pinned() for w in host_waves for n in w)
+        self.h_slot = [torch.empty(slot_bytes, dtype=torch.uint8, pin_memory=True)
+                       for _ in range(self.n_slots)] if need_stage else []
+        self.stream = torch.cuda.Stream(dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        self.ready: "queue.Queue" = queue.Queue()
+        self._released = [None] * len(waves)                   # CUDA events, set by release()
+        self._released_flag = [threading.Event() for _ in waves]
+        self._abort = threading.Event()
+
+    def release(self, wi: int, event: torch.cuda.Event) -> None:
+        self._released[wi] = event
+        self._released_flag[wi].set()
+
+    def abort(self) -> None:
+        self._abort.set()
+
+    def run(self) -> None:
+        try:
+            torch.cuda.set_device(self.dev)
+            h2d_done = []
+            for wi, wave in enumerate(self.waves):
+                slot = wi % self.n_slots
+                if wi >= self.n_slots:
+                    h2d_done[wi - self.n_slots].synchronize()              # pinned staging slot is free again
+                    while not self._released_flag[wi - self.n_slots].wait(0.05):
+                        if self._abort.is_set():
+                            return
+                    self.stream.wait_event(self._released[wi - self.n_slots])   # device slot is free again
+                views, off = {}, 0
+                for n in wave:
+                    t = self.tensors[n]
+                    if t.device.type == "cuda":
+                        views[n] = t.to(self.dev).contiguous()
+                        continue
+                    nb = _nbytes(t)
+                    dv = self.d_slot[slot][off:off + nb].view(t.dtype).view(t.shape)
+                    src = t.detach()
+                    if not src.is_pinned():
+                        hv = self.h_slot[slot][off:off + nb].view(t.dtype).view(t.shape)
+                        N.host_copy(hv, src)
+                        src = hv
+                    with torch.cuda.stream(self.stream):
+                        dv.copy_(src, non_blocking=True)
+                    views[n] = dv
+                    off += _align(nb)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                h2d_done.append(ev)
+                self.ready.put((views, ev))
+        except BaseException as e:                    # surfaces in the consumer
+            self.ready.put(e)
+
+
+class ResultSink:
+    """Takes the device results of a wave to the host on its own stream.
+
+    ``pin_results=False``: ring of three pinned slots + a drain thread that copies each finished slot into ordinary
+    tensors.  ``pin_results=True``: one pinned arena per (wave, dtype), written by the D2H copies directly."""
+
+    def __init__(self, dev: torch.device, slot_bytes: int, n_waves: int, pin_results: bool):
+        self.dev, self.pin = dev, pin_results
+        self.stream = torch.cuda.Stream(dev)
+        self.host: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._inflight = []                                       # pinned mode: (device tensors, D2H-done event)
+        self._ring = [] if pin_results else [torch.empty(max(slot_bytes, 256), dtype=torch.uint8, pin_memory=True)
+                                             for _ in range(min(3, n_waves))]
+        self._q: "queue.Queue" = queue.Queue()
+        self._free = threading.Semaphore(max(1, len(self._ring)))
+        self._err: list = []
+        self._thread = None
+        if not pin_results:
+            self._thread = threading.Thread(target=self._drain, name="awq-drain", daemon=True)
+            self._thread.start()
+
+    def _drain(self) -> None:
+        try:
+            torch.cuda.set_device(self.dev)
+            while True:
+                item = self._q.get()
+                if item is None:
+                    return
+                slot, entries, ev, keep = item
+                ev.synchronize()
+                for name, k, off, nb, dt, shape in entries:
+                    final = torch.empty(shape, dtype=dt)
+                    N.host_copy(final, self._ring[slot][off:off + nb].view(dt).view(shape))
+                    self.host.setdefault(name, {})[k] = final
+                del keep, item
+                self._free.release()
+        except BaseException as e:
+            self._err.append(e)
+            self._free.release()
+
+    def submit(self, wi: int, dev_out: Dict[str, Dict[str, torch.Tensor]], keep, computed: torch.cuda.Event) -> None:
+        """``computed``: recorded after the kernels that produced ``dev_out``; ``keep``: anything that must stay
+        alive until the copies have finished"""
+        if not self.pin:
+            self._free.acquire()                                  # the slot's previous wave has been drained
+            if self._err:
+                raise self._err[0]
+            slot = wi % len(self._ring)
+            entries, off = [], 0
+            self.stream.wait_event(computed)
+            with torch.cuda.stream(self.stream):
+                for name, o in dev_out.items():
+                    for k, v in o.items():
+                        nb = _nbytes(v)
+                        self._ring[slot][off:off + nb].view(v.dtype).view(v.shape).copy_(v, non_blocking=True)
+                        entries.append((name, k, off, nb, v.dtype, tuple(v.shape)))
+                        off += _align(nb)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+            self._q.put((slot, entries, done, (dev_out, keep)))
+            return
+        want: Dict[torch.dtype, int] = {}
+        slots = []
+        for name, o in dev_out.items():
+            for k, v in o.items():
+                off = want.get(v.dtype, 0)
+                slots.append((name, k, v, off))
+                want[v.dtype] = off + _align(_nbytes(v))
+        bufs = {dt: torch.empty(nb, dtype=torch.uint8, pin_memory=True) for dt, nb in want.items()}
+        self.stream.wait_event(computed)
+        with torch.cuda.stream(self.stream):
+            for name, k, v, off in slots:
+                hv = bufs[v.dtype][off:off + _nbytes(v)].view(v.dtype).view(v.shape)
+                hv.copy_(v, non_blocking=True)
+                self.host.setdefault(name, {})[k] = hv
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        self._inflight.append((dev_out, keep, done))
+        if len(self._inflight) > 2:                               # bound the device memory held by finished waves
+            self._inflight[0][2].synchronize()
+            self._inflight.pop(0)
+
+    def close(self, failed: bool = False) -> None:
+        self._q.put(None)
+        if self._thread is not None:
+            self._thread.join(timeout=60 if failed else None)
+        if failed:
+            return
+        if self._err:
+            raise self._err[0]
+        self.stream.synchronize()
+        torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+        self._inflight.clear()
+
+
+def result_bytes(t: torch.Tensor, *, group_size: int, bits: int, n_grid: int, pack: bool, keep_unpacked: bool) -> int:
+    """bytes of one searched tensor's results in a ring slot"""
+    C, K = t.shape
+    G, per = K // group_size, 32 // bits
+    b = _align(C * G * 2) + _align(C * G * 4) + _align(n_grid * 8) + _align(4) + _align(K * 4)
+    if pack:
+        b += _align(C * (-(-K // per)) * 4) + _align(C * (-(-G // per)) * 4)
+    if keep_unpacked:
+        b += _align(C * K * 4)
+    return b
+
+
+def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations: Dict[str, torch.Tensor],
+                               dev: torch.device, *, pack: bool = False, keep_unpacked: Optional[bool] = None,
+                               wave_bytes: int = 256 << 20, pin_results: bool = False) -> Dict[str, Dict[str, torch.Tensor]]:
+    """Every 2-D tensor that has calibration activations goes through the search pipeline (SearchPipeline) and the
+    final K1 pass on W * s_best (column-slab mode).  Results carry the reference's keys plus ``awq_scale`` /
+    ``alpha`` / ``best_idx`` / ``search_err`` (+ ``qweight`` / ``qzeros`` with pack).  ``tensor_q`` (4 bytes per
+    element over PCIe) is produced when ``keep_unpacked`` -- default: only without ``pack``, like the packed path
+    of ``quantize_model``."""
+    from .search import SearchPipeline, _check
+    keep_unpacked = (not pack) if keep_unpacked is None else (keep_unpacked or not pack)
+    names = [n for n, t in tensors.items() if n in activations]
+    for n in names:
+        _check(tensors[n], activations[n], qz.group_size)
+    if not names:
+        return {}
+    waves = plan_waves(names, tensors, wave_bytes)
+    slot_out = max(sum(result_bytes(tensors[n], group_size=qz.group_size, bits=qz.bits, n_grid=qz.n_grid, pack=pack,
+                                    keep_unpacked=keep_unpacked) for n in w) for w in waves)
+    cur = torch.cuda.current_stream(dev)
+    uploader = WaveUploader(dev, tensors, waves)
+    sink = ResultSink(dev, slot_out, len(waves), pin_results)
+    uploader.start()
+    x_dev: Dict[int, torch.Tensor] = {}
+    pipe = SearchPipeline(dev, bits=qz.bits, group_size=qz.group_size, symmetric=qz.symmetric, n_grid=qz.n_grid)
+    try:
+        for wi, wave in enumerate(waves):
+            item = uploader.ready.get()
+            if isinstance(item, BaseException):
+                raise item
+            views, uploaded = item
+            cur.wait_event(uploaded)
+            for n in wave:
+                x = activations[n]
+                if id(x) not in x_dev:
+                    x_dev[id(x)] = x.to(dev, non_blocking=True).contiguous()
+                pipe.submit(n, views[n], x_dev[id(x)])
+            dev_out = {}
+            for name, mean, best, s_best in pipe.finish():
+                s_best = s_best.contiguous()
+                o = qz._quantize_device(views[name], pack=pack, unpacked=keep_unpacked, col_scale=s_best, arith="fp32")
+                o.update({"search_err": mean, "best_idx": best.to(torch.int32), "awq_scale": s_best})
+                dev_out[name] = {k: v for k, v in o.items() if v is not None}
+            computed = torch.cuda.Event()
+            computed.record(cur)
+            uploader.release(wi, computed)
+            sink.submit(wi, dev_out, views, computed)
+        sink.close()
+    except BaseException:
+        uploader.abort()
+        sink.close(failed=True)
+        raise
+    finally:
+        uploader.join(timeout=60)
+    out: Dict[str, Dict[str, torch.Tensor]] = {}
+    for name in names:
+        host = sink.host[name]
+        b = int(host["best_idx"])
+        r = {"tensor_q": host.get("tensor_q"), "scales": host["scales"], "zero_points": host["zero_points"],
+             "bits": torch.tensor(qz.bits, dtype=torch.int32),
+             "group_size": torch.tensor(qz.group_size, dtype=torch.int32),
+             "symmetric": torch.tensor(qz.symmetric, dtype=torch.bool),
+             "awq_scale": host["awq_scale"], "alpha": torch.tensor(b / qz.n_grid, dtype=torch.float32),
+             "best_idx": host["best_idx"], "search_err": host["search_err"]}
+        if r["tensor_q"] is None:
+            del r["tensor_q"]
+        if pack:
+            r["qweight"], r["qzeros"] = host["qweight"], host["qzeros"]
+        out[name] = r
+    return out

@@ -143,3 +143,20 @@ def test_arena_layout_and_short_row_classes():
     assert real.views["b"].shape == (1024,) and float(real.buffers[bf][TILE]) == 1.0
     assert float(real.buffers[bf][3072]) == 0.0 and float(real.buffers[bf][TILE - 1]) == 0.0          # padding is zeroed
     assert real.payload_bytes() == (3072 + 1024 + 10240) * 2
+
+
+def test_stream_wave_planning():
+    """host logic of the streamed model-level AWQ: waves in input order, oversize tensors alone, ring-slot sizing"""
+    from awq_quantizer.quantization import stream
+    t = {"a": torch.zeros(64, 256, dtype=torch.bfloat16), "b": torch.zeros(64, 256, dtype=torch.bfloat16),
+         "big": torch.zeros(512, 1024, dtype=torch.bfloat16), "c": torch.zeros(16, 256, dtype=torch.float16)}
+    assert stream.plan_waves(list(t), t, 70_000) == [["a", "b"], ["big"], ["c"]]
+    assert stream.plan_waves(list(t), t, 1) == [["a"], ["b"], ["big"], ["c"]]
+    assert stream.plan_waves(list(t), t, 1 << 30) == [list(t)]
+    assert stream.plan_waves([], t, 1) == []
+    kw = dict(group_size=128, bits=4, n_grid=20)
+    base = stream.result_bytes(t["a"], pack=False, keep_unpacked=False, **kw)
+    packed = stream.result_bytes(t["a"], pack=True, keep_unpacked=False, **kw)
+    both = stream.result_bytes(t["a"], pack=True, keep_unpacked=True, **kw)
+    assert packed - base == 64 * 32 * 4 + 256 and both - packed == 64 * 256 * 4      # qweight + one padded qzeros slot; int32 codes
+    assert base >= 64 * 2 * 2 + 64 * 2 * 4 + 20 * 8 + 4 + 256 * 4 and base % 256 == 0
