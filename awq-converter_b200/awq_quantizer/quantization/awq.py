@@ -146,8 +146,11 @@ class AWQQuantizer:
             from .search import quantize_with_search
             return quantize_with_search(self, tensor, activations, dev, pack=pack)
 
-        w = tensor.to(dev, non_blocking=True).contiguous()
         keep_unpacked = keep_unpacked or not pack
+        routed = self._quantize_host_pipelined(tensor, dev, pack, keep_unpacked)
+        if routed is not None:
+            return routed
+        w = tensor.to(dev, non_blocking=True).contiguous()
         out = self._quantize_device(w, pack=pack, unpacked=keep_unpacked)
         host = self._to_host({k: v for k, v in out.items() if v is not None}, dev)
         result = {
@@ -161,6 +164,34 @@ class AWQQuantizer:
         if pack:
             result["qweight"] = host["qweight"]
             result["qzeros"] = host["qzeros"]
+        if not keep_unpacked:
+            del result["tensor_q"]
+        return result
+
+    _PIPELINE_MIN_ELEMS = 1 << 20
+
+    def _quantize_host_pipelined(self, tensor: torch.Tensor, dev: torch.device, pack: bool,
+                                 keep_unpacked: bool) -> Optional[Dict[str, torch.Tensor]]:
+        """A large host tensor whose rows are whole groups does not make the upload -> kernel -> download round
+        trip of awq.py:402-412 one after the other: it streams through the native gather pipeline (this thread's
+        pipe: pinned rings, H2D / K1 / D2H overlapped).  None = not applicable, take the plain path."""
+        from .arena import HostArena, arena_eligible, quantize_arena, short_row_len
+        if tensor.device.type != "cpu" or tensor.numel() < self._PIPELINE_MIN_ELEMS:
+            return None
+        shape = tuple(tensor.shape)
+        row_len = 0
+        if not arena_eligible(shape, tensor.dtype, self.group_size, self.bits):
+            row_len = short_row_len(shape, tensor.dtype, self.group_size, self.bits)
+            if not row_len:
+                return None
+        src = {"t": tensor}
+        r = quantize_arena(HostArena.for_tensors(src), bits=self.bits, group_size=self.group_size,
+                           symmetric=self.symmetric, arith=self.arith, device=dev, packed=pack, unpacked=keep_unpacked,
+                           want_zero_points=True, sources=src, pin_results=False, row_len=row_len)["t"]
+        result = {"tensor_q": r.get("tensor_q"), "scales": r["scales"], "zero_points": r["zero_points"],
+                  "bits": r["bits"], "group_size": r["group_size"], "symmetric": r["symmetric"]}
+        if pack:
+            result["qweight"], result["qzeros"] = r["qweight"], r["qzeros"]
         if not keep_unpacked:
             del result["tensor_q"]
         return result

@@ -658,3 +658,31 @@ def test_short_row_tensors_through_gather(native_lib, cuda_device, keep):
             want = O.pack_result(O.group_quant_vec(t, 4, 128, sym, True))
             keys = ("scales", "qweight", "qzeros") + (("tensor_q", "zero_points") if keep else ())
             assert_quant_equal(out[n], want, f"{n}/{sym}", keys=keys)
+
+
+def test_quantize_routes_large_host_tensors_through_the_pipeline(native_lib, cuda_device):
+    """AWQQuantizer.quantize(tensor) -- the reference's own per-tensor call -- streams a large host tensor through
+    the gather pipeline instead of upload -> kernel -> download; same result dict, bit-exact"""
+    cases = [((1100, 1024), "bf16", 4), ((2100, 512), "bf16", 4), ((1 << 20,), "fp16", 4), ((64, 3, 8192), "bf16", 4),
+             ((520, 2048), "fp32", 4), ((1100, 1024), "bf16", 8)]
+    for shape, dt, bits in cases:
+        w = datagen.weights(shape, dt, datagen.seed_of("route", shape, dt, bits))
+        for sym in (False, True):
+            qz = mk(symmetric=sym, bits=bits)
+            assert qz._quantize_host_pipelined(w, cuda_device, False, True) is not None, (shape, dt, bits)
+            want = O.pack_result(O.group_quant_vec(w, bits, 128, sym, True))
+            ref = qz.quantize(w)                                      # unchanged reference call
+            assert sorted(ref) == ["bits", "group_size", "scales", "symmetric", "tensor_q", "zero_points"]
+            assert_quant_equal(ref, want, f"{shape}/{dt}/{bits}/{sym}")
+            assert ref["tensor_q"].shape == w.shape and ref["tensor_q"].dtype == torch.int32
+            assert ref["scales"].shape == want["scales"].shape and ref["zero_points"].dtype == torch.int32
+            both = qz.quantize(w, pack=True)
+            assert_quant_equal(both, want, "both", keys=("tensor_q", "scales", "zero_points", "qweight", "qzeros"))
+            packed = qz.quantize(w, pack=True, keep_unpacked=False)
+            assert "tensor_q" not in packed
+            assert_quant_equal(packed, want, "packed", keys=("scales", "zero_points", "qweight", "qzeros"))
+    small = datagen.weights((64, 1024), "bf16", 3)
+    assert mk()._quantize_host_pipelined(small, cuda_device, False, True) is None          # below the threshold
+    ragged = datagen.weights((4100, 300), "bf16", 4)
+    assert mk()._quantize_host_pipelined(ragged, cuda_device, False, True) is None         # rows are not whole groups
+    assert_quant_equal(mk(symmetric=False).quantize(ragged), O.group_quant_vec(ragged, 4, 128, False, True), "ragged")
