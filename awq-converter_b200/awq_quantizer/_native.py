@@ -32,7 +32,10 @@ SIGNATURES = {
     "awqk_bf16_to_fp16": (_int, [_vp, _vp, _i64, _vp]),
     "awqk_abs_colsum": (_int, [_vp, _int, _i64, _i64, _vp, _vp]),
     "awqk_alpha_grid": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp]),
-    "awqk_fakequant_delta": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _vp, _int, _vp, _vp, _vp]),
+    "awqk_fakequant_delta": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _vp, _int, _vp, _vp]),
+    "awqk_scale_search": (_int, [_vp, _int, _i64, _i64, _vp, _i64, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "awqk_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64, _int, _int, C.POINTER(C.c_size_t)]),
     "awqk_sqerr_gemm": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp]),
     "awqk_export_autoawq": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
     "awqk_pipe_create": (_int, [_int, C.c_size_t, C.POINTER(_vp)]),

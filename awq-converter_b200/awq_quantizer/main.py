@@ -221,8 +221,145 @@ def _apply_config(args: argparse.Namespace, argv) -> None:
     args.skip_layers = list(cfg.get("quantization.skip_layers", []) or [])
 
 
+def select_tensors(index, skip_layers, logger=None):
+    """main.py:243-253 on the header index: (quantizable names largest first, pass-through names).  Non-float,
+    empty and numel < 128 tensors -- and those matching ``quantization.skip_layers`` (default_config.yaml:35) -- are
+    not quantized; the reference drops them, here they are passed through (bf16 -> fp16 by K3, others unchanged)."""
+    quant, passthrough = [], []
+    for name, info in index.items():
+        floating = info.dtype is not None and info.dtype.is_floating_point
+        if any(s in name for s in skip_layers):
+            passthrough.append(name)
+        elif not floating or info.numel == 0:
+            if logger:
+                logger.warning(f"Skipping invalid tensor: {name}")
+            passthrough.append(name)
+        elif info.numel < 128:
+            if logger:
+                logger.warning(f"Skipping tensor too small for grouping: {name}")
+            passthrough.append(name)
+        else:
+            quant.append(name)
+    quant.sort(key=lambda n: index[n].nbytes, reverse=True)
+    return quant, passthrough
+
+
+def convert_passthrough(tensors: Dict[str, torch.Tensor], device: str) -> Dict[str, torch.Tensor]:
+    """the tensors that are NOT quantized: bf16 -> fp16 through K3 (tensor_utils.py:10-22, the conversion the
+    reference's loader offers at safetensors_loader.py:205-225), everything else unchanged"""
+    from .utils.tensor_utils import convert_bf16_to_fp16
+    return {n: (convert_bf16_to_fp16(t, device=device) if t.dtype == torch.bfloat16 and t.numel() else t)
+            for n, t in tensors.items()}
+
+
+def save_passthrough(tensors: Dict[str, torch.Tensor], output_dir: str, rank: int, world: int) -> Optional[str]:
+    if not tensors:
+        return None
+    from safetensors.torch import save_file
+    fn = (f"rank{rank}_" if world > 1 else "") + "passthrough.safetensors"
+    save_file({n: t.contiguous() for n, t in tensors.items()}, os.path.join(output_dir, fn))
+    return fn
+
+
+def _rank_work(args, logger, rank: int, world: int, local: int) -> dict:
+    """Everything one process does; returns its metadata record (with 'error' set on failure) and never raises:
+    under torchrun every rank must reach the metadata gather, or the others would wait in it."""
+    meta = {"rank": rank, "num_chunks": 0, "chunk_size": args.chunk_size, "tensor_to_chunk": {}, "num_tensors": 0,
+            "format": "safetensors" if args.save_safetensors else "pytorch", "quantization_params": None, "files": [],
+            "passthrough": {}, "error": None}
+    try:
+        if world > 1:
+            devices = [f"cuda:{parallel.local_device_index(local)}"]
+        elif args.multi_gpu or args.device.lower() == "all":
+            devices = get_available_gpus(logger)
+        else:
+            devices = [args.device]
+        if not devices or any(not d.startswith("cuda") for d in devices) or not torch.cuda.is_available():
+            meta["error"] = ("This build of awq_quantizer runs on CUDA (B200) only; no CPU execution path exists "
+                             f"(requested devices: {devices or 'none found'})")
+            return meta
+        for d in devices:
+            idx = int(d.split(":")[1]) if ":" in d else torch.cuda.current_device()
+            tot, free = get_device_memory_info(idx)
+            logger.info(f"Using GPU {d}: {torch.cuda.get_device_name(idx)} ({tot:.1f} GB total, {free:.1f} GB free)")
+
+        logger.info(f"Loading model from {args.model_id}")
+        try:
+            loader = load_model_from_hub(args.model_id, logger_level=args.log_level)
+            index = loader.index()                       # headers only: nothing is read before the partition is known
+        except Exception as e:
+            meta["error"] = f"Failed to load model: {e}"
+            return meta
+        quant_names, pass_names = select_tensors(index, args.skip_layers, logger)
+        if world > 1:                                    # rank-local shard (torchrun): by bytes, largest first
+            costs = [(n, index[n].nbytes) for n in quant_names] + [(n, index[n].nbytes) for n in pass_names]
+            mine = set(parallel.shard_for_rank(costs, world, rank))
+            quant_names = [n for n in quant_names if n in mine]
+            pass_names = [n for n in pass_names if n in mine]
+        try:                                             # only this rank's tensors, as views of the mapped files
+            tensors = loader.load_tensors(names=quant_names + pass_names)
+        except Exception as e:
+            meta["error"] = f"Failed to load model: {e}"
+            return meta
+        quantizable = {n: tensors[n] for n in quant_names}
+        shards = [quantizable] if world > 1 else partition_tensors(quantizable, len(devices))
+
+        calib = {}
+        if args.calibration_file:
+            if args.scale_method != "mse":
+                logger.warning("--calibration_file is ignored: the activation-aware search belongs to scale_method=mse")
+            else:
+                from safetensors.torch import load_file
+                calib = load_file(args.calibration_file)
+                logger.info(f"Loaded calibration activations for {len(calib)} tensors")
+
+        def run_device(device: str, shard: Dict[str, torch.Tensor]) -> Dict[str, dict]:
+            qz = AWQQuantizer(bits=args.bits, group_size=args.group_size, symmetric=args.symmetric,
+                              zero_point=args.zero_point, percentile=args.percentile, scale_method=args.scale_method,
+                              per_channel=args.per_channel, device=device, logger_name=f"awq_quantizer_{device}",
+                              logger_level=args.log_level, logger_to_file=args.log_file is not None,
+                              logger_file_path=args.log_file, arith=args.arith, n_grid=args.n_grid)
+            for name in shard:
+                logger.info(f"Quantizing tensor: {name} on {device}")
+            # the whole shard in ONE call: searched linears stream in waves (quantization/stream.py), every other
+            # whole-group tensor through the native gather pipeline (bounded pinned rings, no per-tensor upload /
+            # kernel / download round trip as in main.py:333-392); what neither can take (ragged rows ...) falls
+            # back to per-tensor calls inside.  --batch_size / --num_workers / --prefetch_factor are accepted for
+            # compatibility and not needed.
+            acts = {n: calib[n] for n, t in shard.items() if n in calib and t.dim() == 2}
+            try:
+                return qz.quantize_model(shard, activations=acts or None, pack=args.pack, keep_unpacked=True)
+            except Exception as e:
+                logger.error(f"Error processing shard on {device}: {e}")
+                return {}
+
+        quantized: Dict[str, dict] = {}
+        if len(devices) == 1:
+            quantized = run_device(devices[0], shards[0])
+        else:
+            with ThreadPoolExecutor(max_workers=len(devices)) as ex:
+                for part in ex.map(lambda ds: run_device(*ds), zip(devices, shards)):
+                    quantized.update(part)
+        logger.info(f"Successfully quantized {len(quantized)} tensors")
+        try:
+            saved = save_model_in_chunks(quantized, args.output_dir, args.chunk_size, args.save_safetensors, logger,
+                                         rank=rank, world=world, write_metadata=False)
+            passed = convert_passthrough({n: tensors[n] for n in pass_names}, devices[0])
+            fn = save_passthrough(passed, args.output_dir, rank, world)
+        except Exception as e:
+            meta["error"] = f"Failed to save quantized model: {e}"
+            return meta
+        meta.update(saved)
+        meta["passthrough"] = {n: fn for n in passed}
+        return meta
+    except Exception as e:                               # anything unexpected still reaches the gather
+        meta["error"] = f"Error during quantization: {e}"
+        return meta
+
+
 def main(argv=None) -> int:
     logger = None
+    dist_up = False
     try:
         import sys
         argv = sys.argv[1:] if argv is None else list(argv)
@@ -233,103 +370,35 @@ def main(argv=None) -> int:
                             file_path=args.log_file)
         os.makedirs(args.output_dir, exist_ok=True)
         rank, world = parallel.init_distributed()
+        dist_up = world > 1
         local = parallel.rank_info()[2]
-        if world > 1:
-            parallel.bind_to_gpu_numa(local)
-
-        if world > 1:
-            devices = [f"cuda:{local}"]
-        elif args.multi_gpu or args.device.lower() == "all":
-            devices = get_available_gpus(logger)
-        else:
-            devices = [args.device]
-        if not devices or any(not d.startswith("cuda") for d in devices) or not torch.cuda.is_available():
-            logger.error("This build of awq_quantizer runs on CUDA (B200) only; no CPU execution path exists "
-                         f"(requested devices: {devices or 'none found'})")
-            return 1
-        for d in devices:
-            idx = int(d.split(":")[1]) if ":" in d else torch.cuda.current_device()
-            tot, free = get_device_memory_info(idx)
-            logger.info(f"Using GPU {d}: {torch.cuda.get_device_name(idx)} ({tot:.1f} GB total, {free:.1f} GB free)")
-
-        logger.info(f"Loading model from {args.model_id}")
-        try:
-            tensors = load_model_from_hub(args.model_id, logger_level=args.log_level).load_tensors()
-        except Exception as e:
-            logger.error(f"Failed to load model: {e}")
-            return 1
-        if args.skip_layers:
-            tensors = {n: t for n, t in tensors.items() if not any(s in n for s in args.skip_layers)}
-
+        if world > 1 and torch.cuda.is_available():
+            parallel.bind_to_gpu_numa(parallel.local_device_index(local))
         start = time.time()
-        quantizable = {n: t for b in prepare_tensors_for_quantization(tensors, devices[0], args.max_memory, 1 << 30, None)
-                       for n, t in b.items()}
-        if world > 1:                                    # rank-local shard (torchrun)
-            mine = set(parallel.shard_for_rank(parallel.tensor_costs(quantizable), world, rank))
-            shards = [{n: t for n, t in quantizable.items() if n in mine}]
-        else:                                            # one process, 1..N devices
-            shards = partition_tensors(quantizable, len(devices))
-
-        calib = {}
-        if args.calibration_file:
-            from safetensors.torch import load_file
-            calib = load_file(args.calibration_file)
-            logger.info(f"Loaded calibration activations for {len(calib)} tensors")
-
-        def run_device(device: str, shard: Dict[str, torch.Tensor]) -> Dict[str, dict]:
-            qz = AWQQuantizer(bits=args.bits, group_size=args.group_size, symmetric=args.symmetric,
-                              zero_point=args.zero_point, percentile=args.percentile, scale_method=args.scale_method,
-                              per_channel=args.per_channel, device=device, logger_name=f"awq_quantizer_{device}",
-                              logger_level=args.log_level, logger_to_file=args.log_file is not None,
-                              logger_file_path=args.log_file, arith=args.arith, n_grid=args.n_grid)
-            done: Dict[str, dict] = {}
-            searched = {n: t for n, t in shard.items() if n in calib and t.dim() == 2}
-            if searched:
-                done.update(qz.quantize_model(searched, activations={n: calib[n] for n in searched}, pack=args.pack,
-                                              keep_unpacked=True))
-                shard = {n: t for n, t in shard.items() if n not in done}
-            # the whole shard in ONE call: every whole-group tensor streams through the native gather pipeline
-            # (bounded pinned rings, no per-tensor upload / kernel / download round trip as in main.py:333-392);
-            # what it cannot take (ragged rows, tiny tensors ...) falls back to per-tensor calls inside.
-            # --batch_size / --num_workers / --prefetch_factor are accepted for compatibility and not needed.
-            for name in shard:
-                logger.info(f"Quantizing tensor: {name} on {device}")
-            try:
-                done.update(qz.quantize_model(shard, pack=args.pack, keep_unpacked=True))
-            except Exception as e:
-                logger.error(f"Error processing shard on {device}: {e}")
-            return done
-
-        quantized: Dict[str, dict] = {}
-        if len(devices) == 1:
-            quantized = run_device(devices[0], shards[0])
-        else:
-            with ThreadPoolExecutor(max_workers=len(devices)) as ex:
-                for part in ex.map(lambda ds: run_device(*ds), zip(devices, shards)):
-                    quantized.update(part)
-
-        if world == 1 and not quantized:
+        meta = _rank_work(args, logger, rank, world, local)
+        if meta["error"]:
+            logger.error(meta["error"])
+        metas = parallel.gather_metadata(meta)           # every rank arrives here, failed or not
+        errors = [m for m in metas if m.get("error")]
+        merged = parallel.merge_chunk_maps([m for m in metas if not m.get("error")])
+        if rank == 0 and not (world == 1 and errors):
+            passthrough = {}
+            for m in metas:
+                passthrough.update(m.get("passthrough") or {})
+            merged.update({"chunk_size": args.chunk_size, "format": meta["format"],
+                           "quantization_params": next((m["quantization_params"] for m in metas
+                                                        if m.get("num_tensors") and m.get("quantization_params")), None),
+                           "passthrough": passthrough})
+            if world > 1:
+                merged["world_size"] = world
+                merged["failed_ranks"] = [m["rank"] for m in errors]
+            with open(os.path.join(args.output_dir, "metadata.json"), "w") as f:
+                json.dump(merged, f, indent=2)
+        if errors:
+            return 1
+        if not merged["num_tensors"]:
             logger.error("No tensors were successfully quantized")
             return 1
-        logger.info(f"Successfully quantized {len(quantized)} tensors")
-        try:
-            meta = save_model_in_chunks(quantized, args.output_dir, args.chunk_size, args.save_safetensors, logger,
-                                        rank=rank, world=world)
-        except Exception as e:
-            logger.error(f"Failed to save quantized model: {e}")
-            return 1
-        if world > 1:
-            metas = parallel.gather_metadata(meta)
-            if rank == 0:
-                merged = parallel.merge_chunk_maps(metas)
-                merged.update({"chunk_size": args.chunk_size, "format": meta["format"], "world_size": world,
-                               "quantization_params": next((m["quantization_params"] for m in metas if m["num_tensors"]),
-                                                           meta["quantization_params"])})
-                with open(os.path.join(args.output_dir, "metadata.json"), "w") as f:
-                    json.dump(merged, f, indent=2)
-                if not merged["num_tensors"]:
-                    logger.error("No tensors were successfully quantized")
-                    return 1
         logger.info(f"Quantization complete in {time.time() - start:.2f} seconds")
         return 0
     except SystemExit:
@@ -340,6 +409,14 @@ def main(argv=None) -> int:
         else:
             print(f"Error during quantization: {e}")
         return 1
+    finally:
+        if dist_up:
+            try:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.destroy_process_group()
+            except Exception:
+                pass
 
 
 if __name__ == "__main__":

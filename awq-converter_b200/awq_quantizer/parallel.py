@@ -29,13 +29,22 @@ def init_distributed(backend: Optional[str] = None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            # AWQ_DIST_BACKEND=gloo: ranks that share a GPU (fewer devices than ranks; NCCL refuses duplicates)
+            backend = os.environ.get("AWQ_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
         kwargs = {}
         if backend == "nccl":
             torch.cuda.set_device(local)
             kwargs["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend, rank=rank, world_size=world, **kwargs)
     return rank, world
+
+
+def local_device_index(local_rank: int) -> int:
+    """the CUDA device of a local rank: its own GPU; ranks beyond the device count wrap around (sharing a GPU
+    works for this path -- no collective runs on the device -- and is what a 1-GPU test box needs)"""
+    import torch
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    return local_rank % n if n else local_rank
 
 
 def bind_to_gpu_numa(device_index: int) -> Optional[int]:

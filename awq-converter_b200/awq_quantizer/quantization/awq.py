@@ -142,6 +142,9 @@ class AWQQuantizer:
         self._check_zero_point_mode()
         if tensor.numel() == 0:
             raise RuntimeError("cannot quantize an empty tensor (reference: min() of an empty tensor)")
+        if activations is not None and self.scale_method != "mse":
+            self.logger.warning("activations are ignored: the activation-aware search belongs to scale_method='mse'")
+            activations = None
         if activations is not None:
             from .search import quantize_with_search
             return quantize_with_search(self, tensor, activations, dev, pack=pack)
@@ -264,19 +267,36 @@ class AWQQuantizer:
         other tensors take the paths above.  With ``pack`` the results carry ``tensor_q`` / ``zero_points`` only
         if ``keep_unpacked`` is true (4 more bytes per element over PCIe)."""
         pin = self._pin_now() if _pin is None else _pin          # one decision per model
+        if activations and self.scale_method != "mse":
+            self.logger.warning("activations are ignored: the activation-aware search belongs to scale_method='mse'")
+            activations = None
         if activations:
             from .search import quantize_model_with_search
             dev = self._cuda_device()
             self._check_zero_point_mode()
+            want = {n: t for n, t in tensors.items() if n in activations}
             searched = {}
             try:
-                searched = quantize_model_with_search(self, {n: t for n, t in tensors.items() if n in activations},
-                                                      activations, dev, pack=pack, keep_unpacked=keep_unpacked,
+                searched = quantize_model_with_search(self, want, activations, dev, pack=pack, keep_unpacked=keep_unpacked,
                                                       pin_results=bool(self.pin_results))
             except Exception as e:
-                self.logger.error(f"Activation-aware search failed: {e}")
+                # the streamed model-level search failed as a whole (e.g. one bad shape, out of memory): search tensor
+                # by tensor instead, so that one offender cannot silently turn AWQ scaling off for all the others
+                self.logger.error(f"Streamed activation-aware search failed ({e}); searching tensor by tensor")
+                torch.cuda.synchronize(dev)
+                keep = (not pack) if keep_unpacked is None else bool(keep_unpacked or not pack)
+                for name, t in want.items():
+                    try:
+                        r = self.quantize(t, activations=activations[name], pack=pack)
+                        if not keep:
+                            r.pop("tensor_q", None)
+                        searched[name] = r
+                    except Exception as e2:
+                        self.logger.error(f"Activation-aware search failed for {name}: {e2}; quantizing it without "
+                                          f"AWQ scaling (no 'awq_scale' in its result)")
             rest = {n: t for n, t in tensors.items() if n not in searched}
-            other = self.quantize_model(rest, pack=pack, chunk_bytes=chunk_bytes, pipeline=pipeline, _pin=pin) if rest else {}
+            other = self.quantize_model(rest, pack=pack, chunk_bytes=chunk_bytes, pipeline=pipeline,
+                                        keep_unpacked=keep_unpacked, _pin=pin) if rest else {}
             return {n: (searched[n] if n in searched else other[n]) for n in tensors if n in searched or n in other}
         if not pack:
             from .arena import HostArena, pipe_eligible, quantize_arena
@@ -329,12 +349,30 @@ class AWQQuantizer:
                 else:
                     singles[name] = t
             arena = HostArena.for_tensors(flat) if flat else None
+        rest = {}
+
+        def guarded(names, fn):
+            """one pipelined section; on failure the pipe is drained BEFORE its half-written buffers are dropped
+            (asynchronous D2H copies may still target them) and the tensors take the per-tensor path"""
+            try:
+                quantized.update(fn())
+            except Exception as e:
+                self.logger.error(f"Pipelined quantization failed ({e}); using the per-tensor path for {len(names)} tensors")
+                try:
+                    sync_pipe(dev, chunk_bytes)
+                except Exception:
+                    torch.cuda.synchronize(dev)
+                for n in names:
+                    quantized.pop(n, None)
+                    rest[n] = names[n]
+
         if arena is not None:
-            quantized.update(quantize_arena(arena, bits=self.bits, group_size=self.group_size,
-                                            symmetric=self.symmetric, arith=self.arith, device=dev,
-                                            chunk_bytes=chunk_bytes, sync=False, unpacked=keep, want_zero_points=keep,
-                                            sources=None if isinstance(tensors, HostArena) else flat,
-                                            pin_results=isinstance(tensors, HostArena) or pin))
+            src = None if isinstance(tensors, HostArena) else flat
+            guarded(src if src is not None else {n: arena.views[n] for n in arena.specs},
+                    lambda: quantize_arena(arena, bits=self.bits, group_size=self.group_size,
+                                           symmetric=self.symmetric, arith=self.arith, device=dev,
+                                           chunk_bytes=chunk_bytes, sync=False, unpacked=keep, want_zero_points=keep,
+                                           sources=src, pin_results=isinstance(tensors, HostArena) or pin))
         # rows of 1 / 2 / 4 groups (K = 512 at g = 128): gather pipeline too, one class per row length
         short: Dict[int, Dict[str, torch.Tensor]] = {}
         for name, tensor in list(singles.items()):
@@ -344,20 +382,26 @@ class AWQQuantizer:
                 if k:
                     short.setdefault(k, {})[name] = singles.pop(name)
         for k, group in short.items():
-            quantized.update(quantize_arena(HostArena.for_tensors(group), bits=self.bits, group_size=self.group_size,
-                                            symmetric=self.symmetric, arith=self.arith, device=dev,
-                                            chunk_bytes=chunk_bytes, sync=False, unpacked=keep, want_zero_points=keep,
-                                            sources=group, pin_results=pin, row_len=k))
-        rest = {}
+            guarded(group, lambda k=k, group=group: quantize_arena(
+                HostArena.for_tensors(group), bits=self.bits, group_size=self.group_size, symmetric=self.symmetric,
+                arith=self.arith, device=dev, chunk_bytes=chunk_bytes, sync=False, unpacked=keep,
+                want_zero_points=keep, sources=group, pin_results=pin, row_len=k))
         for name, tensor in singles.items():           # rows of whole groups: same pipeline, chunked by rows
             if not keep and isinstance(tensor, torch.Tensor) and tensor.device.type == "cpu" and \
                     pipe_eligible(tuple(tensor.shape), tensor.dtype, self.group_size, self.bits):
-                r = quantize_rows_pipelined(tensor, bits=self.bits, group_size=self.group_size, symmetric=self.symmetric,
-                                            arith=self.arith, device=dev, chunk_bytes=chunk_bytes, sync=False)
-                quantized[name] = r
+                guarded({name: tensor}, lambda name=name, tensor=tensor: {name: quantize_rows_pipelined(
+                    tensor, bits=self.bits, group_size=self.group_size, symmetric=self.symmetric, arith=self.arith,
+                    device=dev, chunk_bytes=chunk_bytes, sync=False)})
             else:
                 rest[name] = tensor
-        sync_pipe(dev, chunk_bytes)
+        try:
+            sync_pipe(dev, chunk_bytes)
+        except Exception as e:                         # an asynchronous failure surfaces here: nothing queued is trusted
+            self.logger.error(f"Pipelined quantization failed at the final synchronisation ({e}); using the per-tensor path")
+            torch.cuda.synchronize(dev)
+            for n in list(quantized):
+                quantized.pop(n)
+            rest = dict(tensors.items()) if not isinstance(tensors, HostArena) else {n: arena.views[n] for n in arena.specs}
         for r in quantized.values():
             r.pop("_keepalive", None)
         for name, tensor in rest.items():              # ragged rows, odd group sizes, fp64, numel < group_size ...

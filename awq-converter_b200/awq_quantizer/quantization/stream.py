@@ -227,7 +227,7 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
     ``alpha`` / ``best_idx`` / ``search_err`` (+ ``qweight`` / ``qzeros`` with pack).  ``tensor_q`` (4 bytes per
     element over PCIe) is produced when ``keep_unpacked`` -- default: only without ``pack``, like the packed path
     of ``quantize_model``."""
-    from .search import SearchPipeline, _check
+    from .search import SearchPipeline, _check, alloc_outputs
     keep_unpacked = (not pack) if keep_unpacked is None else (keep_unpacked or not pack)
     names = [n for n, t in tensors.items() if n in activations]
     for n in names:
@@ -250,17 +250,19 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
                 raise item
             views, uploaded = item
             cur.wait_event(uploaded)
+            wave_out = {}
             for n in wave:
                 x = activations[n]
                 if id(x) not in x_dev:
                     x_dev[id(x)] = x.to(dev, non_blocking=True).contiguous()
-                pipe.submit(n, views[n], x_dev[id(x)])
+                C, K = views[n].shape
+                wave_out[n] = alloc_outputs(qz, C, K, dev, pack=pack, unpacked=keep_unpacked)
+                pipe.submit(n, views[n], x_dev[id(x)], outputs=wave_out[n])      # scores + argmin + final K1 pass
             dev_out = {}
-            for name, mean, best, s_best in pipe.finish():
-                s_best = s_best.contiguous()
-                o = qz._quantize_device(views[name], pack=pack, unpacked=keep_unpacked, col_scale=s_best, arith="fp32")
-                o.update({"search_err": mean, "best_idx": best.to(torch.int32), "awq_scale": s_best})
-                dev_out[name] = {k: v for k, v in o.items() if v is not None}
+            for name, mean, best, s_best in pipe.finish(keep_grids=True):
+                o = dict(wave_out[name])
+                o.update({"search_err": mean, "best_idx": best, "awq_scale": s_best})
+                dev_out[name] = o
             computed = torch.cuda.Event()
             computed.record(cur)
             uploader.release(wi, computed)

@@ -1,0 +1,391 @@
+// K2 fused: the scores  err_i = sum_{t,c} ( X . dW_i^T )^2  of one tensor for the whole alpha grid in ONE persistent
+// kernel -- the fake-quant delta operand is produced by warps of the same CTAs that run the tcgen05 GEMM, while
+// the tensor pipe is busy, instead of by a separate kernel that writes [n_grid, C, K] bf16 to HBM first.
+//
+//   CTA pair (cluster of 2, one per SM pair, persistent):
+//     warps 0-7   PRODUCERS   dW units: 8 rows x 512 columns of one slab (256 W rows x K for one alpha), the
+//                             same arithmetic as the stand-alone kernel (delta16, awqk_search.cuh) -> ring slot
+//                             in global memory (L2 resident) -> ready[slab] += 1 (release)
+//     warps 8-11  EPILOGUE    tcgen05.ld of the accumulator, sum of squares, one fp64 atomic per warp and tile
+//     warp  12    TMA         waits ready[slab] == units (acquire + cross-proxy fence), then streams X and dW
+//                             k-blocks into the 6-stage SWIZZLE_128B ring (cp.async.bulk.tensor, cta_group::2)
+//     warp  13    MMA         leader CTA only: tcgen05.mma.cta_group::2 (M = 256 across the pair, N = 256),
+//                             TMEM double buffered; after the last k-block of a tile has LANDED it adds 1 to
+//                             done[slab] (release): the ring slot may be overwritten once all m-tiles are done
+//
+//   slab q = n_tile * n_grid + alpha (alpha fastest: the 256 W rows stay hot for the whole grid);
+//   tile  = q * m_tiles + m_tile -> the m_tiles pairs that consume a slab run side by side;
+//   units are dealt round-robin to all producer warps of the grid in slab order, so production runs a few slabs
+//   ahead of consumption and is throttled only by the ring (slot of slab q is reused by slab q + ring).
+//
+// Progress: the lowest unfinished unit never waits on anything later than itself, so the
+// kernel cannot deadlock as long as all CTAs are resident -- it is launched cooperatively, with at most
+// cudaOccupancyMaxActiveClusters pairs.  Every wait is bounded (trap after 8 s) so that a protocol bug faults
+// instead of hanging the device.
+#include <algorithm>
+#include <atomic>
+
+#include "awqk_search.cuh"
+#include "awqk_tc.cuh"
+
+namespace awqk {
+
+constexpr int kfBM = 128, kfBN = 256, kfBNh = 128, kfBK = 64;   // per-CTA A rows, pair N, per-CTA B rows
+constexpr int kfStages = 6;
+constexpr int kfABytes = kfBM * kfBK * 2;
+constexpr int kfBBytes = kfBNh * kfBK * 2;
+constexpr int kfStageBytes = kfABytes + kfBBytes;
+constexpr int kfProducerWarps = 8;
+constexpr int kfThreads = (kfProducerWarps + 6) * 32;           // 448
+constexpr uint32_t kfTmemCols = 512;
+constexpr int kfSlabRows = 256;
+constexpr int kfUnitRows = 8, kfUnitCols = 512;
+
+// ---- bounded waits (a protocol bug must fault, not hang the device) --------------------------------------------
+constexpr unsigned long long kfWaitLimitNs = 8000000000ull;    // 8 s
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mb_wait_bounded(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  unsigned long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000000u)
+        : "memory");
+    if (!ok) {
+      const unsigned long long t = global_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > kfWaitLimitNs) __trap();
+    }
+  } while (!ok);
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void wait_counter(const uint32_t* p, uint32_t target) {
+  if (ld_acquire_gpu(p) >= target) return;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_gpu(p) < target) {
+    __nanosleep(200);
+    if (global_ns() - t0 > kfWaitLimitNs) __trap();
+  }
+}
+
+template <typename WT, int G, int BITS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kfThreads, 1)
+search_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ring,
+                    const WT* __restrict__ w, const float* __restrict__ s_grid, __nv_bfloat16* __restrict__ ring_base,
+                    int64_t C, int K, int n_grid, int mp_tiles, int n_tiles, int k_blocks, int ring, int sym_i,
+                    uint32_t* __restrict__ ready, uint32_t* __restrict__ done, double* __restrict__ err) {
+  extern __shared__ uint8_t kf_raw[];
+  const uint32_t raw = s2u(kf_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;               // identical offset in both CTAs of the pair
+  uint8_t* gsm = kf_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + kfStages * kfStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kfStages + 4);
+  const uint32_t full0 = s2u(bars), empty0 = full0 + 8 * kfStages;
+  const uint32_t tfull0 = empty0 + 8 * kfStages, tempty0 = tfull0 + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();                        // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_slabs = n_tiles * n_grid;
+  const int total_tiles = n_slabs * mp_tiles;
+  const int col_blocks = (K + kfUnitCols - 1) / kfUnitCols;
+  const int units_per_slab = (kfSlabRows / kfUnitRows) * col_blocks;
+  constexpr int kTmaWarp = kfProducerWarps + 4, kMmaWarp = kfProducerWarps + 5;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kfStages; ++s) {
+      mb_init(full0 + 8 * s, 1);
+      mb_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mb_init(tfull0 + 8 * a, 1);
+      mb_init(tempty0 + 8 * a, 8);                             // 4 epilogue warps x 2 CTAs (used on the leader)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {   // the same logical warp in both CTAs allocates (and later frees) the pair's TMEM
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)),
+                 "r"(kfTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                          // peer barriers are initialised before any remote signal
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp < kfProducerWarps) {
+    // ===================== delta producers =====================
+    const bool sym = sym_i != 0;
+    const float qmin = sym ? -(float)(1 << (BITS - 1)) : 0.0f;
+    const float qmax = sym ? (float)((1 << (BITS - 1)) - 1) : (float)((1 << BITS) - 1);
+    const int64_t n_units = (int64_t)n_slabs * units_per_slab;
+    const int64_t stride = (int64_t)gridDim.x * kfProducerWarps;
+    int checked = -1;                                          // last slab whose ring slot was seen free
+#pragma unroll 1
+    for (int64_t v = (int64_t)blockIdx.x * kfProducerWarps + warp; v < n_units; v += stride) {
+      const int q = (int)(v / units_per_slab);
+      const int u = (int)(v - (int64_t)q * units_per_slab);
+      const int rb = u / col_blocks, cb = u - rb * col_blocks;
+      const int nt = q / n_grid, a = q - nt * n_grid;
+      const int slot = q % ring;
+      if (q >= ring && q != checked) {                         // every m-tile of the slab that used this slot has landed
+        if (lane == 0) wait_counter(done + (q - ring), (uint32_t)mp_tiles);
+        __syncwarp();
+        checked = q;
+      }
+      const int col = cb * kfUnitCols + lane * 16;
+      const bool cvalid = col < K;
+      float2 sv[8], rs[8];
+      if (cvalid) {
+        const float4* sp = reinterpret_cast<const float4*>(s_grid + (int64_t)a * K + col);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 t = __ldg(sp + c);
+          sv[2 * c] = make_float2(t.x, t.y);
+          sv[2 * c + 1] = make_float2(t.z, t.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sv[i] = make_float2(1.0f, 1.0f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rs[i] = make_float2(refined_rcp(sv[i].x), refined_rcp(sv[i].y));
+      const int64_t row0 = (int64_t)nt * kfSlabRows + rb * kfUnitRows;
+      const WT* wp = w + row0 * K + col;
+      __nv_bfloat16* dst = ring_base + ((int64_t)slot * kfSlabRows + rb * kfUnitRows) * K + col;
+      Raw16<WT> nxt;
+      if (cvalid && row0 < C) nxt.load(wp); else nxt.zero();
+#pragma unroll 1
+      for (int r = 0; r < kfUnitRows; ++r) {
+        const Raw16<WT> cur = nxt;
+        if (r + 1 < kfUnitRows) {
+          if (cvalid && row0 + r + 1 < C) nxt.load(wp + (int64_t)(r + 1) * K); else nxt.zero();
+        }
+        uint32_t o[8];
+        if (row0 + r < C) {                                    // warp uniform
+          float2 wv[8];
+          cur.unpack(wv);
+          delta16<G, BITS>(wv, sv, [&](int i) { return rs[i]; }, sym, qmin, qmax, o);
+        } else {                                               // rows past C: the slot is reused, write the zeros
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = 0u;
+        }
+        if (cvalid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + (int64_t)r * K);
+          d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      // generic-proxy writes -> visible to the TMA (async proxy) reads of other SMs: fence, then release
+      __threadfence();
+      fence_proxy_async_global();
+      __syncwarp();
+      if (lane == 0) red_release_gpu_add(ready + q, 1u);
+    }
+  } else if (warp == kTmaWarp) {
+    // ===================== TMA (both CTAs; completion lands on the LEADER's full barrier) ==========
+    if (lane == 0) {
+      uint32_t stage = 0, ph = 1;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        const int q = tile / mp_tiles;
+        const int mp = tile - q * mp_tiles;
+        const int slot = q % ring;
+        wait_counter(ready + q, (uint32_t)units_per_slab);     // the whole slab has been produced
+        fence_proxy_async_global();
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mb_wait_bounded(empty0 + 8 * stage, ph);             // own slot free (multicast commit from the leader)
+          const uint32_t lbar = (full0 + 8 * stage) & kPeerMask;
+          if (rank == 0) mb_expect_tx(full0 + 8 * stage, 2 * kfStageBytes);
+          const uint32_t sa = base + stage * kfStageBytes;
+          tma2_load_2d(sa, &map_x, kb * kfBK, mp * 256 + (int)rank * kfBM, lbar);
+          tma2_load_3d(sa + kfABytes, &map_ring, kb * kfBK, (int)rank * kfBNh, slot, lbar);
+          if (++stage == kfStages) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer: one thread of the leader CTA =====================
+    if (rank == 0) {
+      uint32_t stage = 0, ph = 0;
+      int it = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+        const int q = tile / mp_tiles;
+        const uint32_t ab = (uint32_t)it & 1u;
+        const uint32_t aph = ((uint32_t)it >> 1) & 1u;
+        mb_wait_bounded(tempty0 + 8 * ab, aph ^ 1u);           // both CTAs' epilogues drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + ab * kfBN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mb_wait_bounded(full0 + 8 * stage, ph);              // both CTAs' A and B halves have landed
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t sa = base + stage * kfStageBytes;
+            const uint64_t adesc = desc_sw128(sa);
+            const uint64_t bdesc = desc_sw128(sa + kfABytes);
+#pragma unroll
+            for (int k = 0; k < kfBK / 16; ++k) umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, (kb | k) ? 1u : 0u);
+            umma2_commit_mc(empty0 + 8 * stage);               // frees the slot in BOTH CTAs
+            if (kb == k_blocks - 1) {
+              umma2_commit_mc(tfull0 + 8 * ab);
+              red_release_gpu_add(done + q, 1u);               // the slab's last k-block is in shared memory
+            }
+          }
+          __syncwarp();
+          if (++stage == kfStages) { stage = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs): sum of squares of this CTA's 128 x 256 half ==========
+    const uint32_t quarter = (uint32_t)warp & 3u;
+    int it = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
+      const int a = (tile / mp_tiles) % n_grid;
+      const uint32_t ab = (uint32_t)it & 1u;
+      const uint32_t aph = ((uint32_t)it >> 1) & 1u;
+      mb_wait_bounded(tfull0 + 8 * ab, aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ab * kfBN + ((quarter * 32u) << 16);
+      float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < kfBN; c += 64) {
+        uint32_t v0[32], v1[32];
+        tm_ld32(taddr + c, v0);
+        tm_ld32(taddr + c + 32, v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float f0 = __uint_as_float(v0[j]), f1 = __uint_as_float(v1[j]);
+          acc0 = __fmaf_rn(f0, f0, acc0);
+          acc1 = __fmaf_rn(f1, f1, acc1);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mb_arrive_cluster(tempty0 + 8 * ab, 0);   // tell the leader this half is drained
+      double d = (double)acc0 + (double)acc1;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);
+      if (lane == 0) atomicAdd(err + a, d);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                          // nobody leaves while the peer may still signal us
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kfTmemCols) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+size_t fused_slab_bytes(int64_t K) { return (size_t)kfSlabRows * (size_t)K * 2; }
+
+size_t fused_sync_bytes(int64_t C, int n_grid) {
+  return (size_t)ceil_div(C, kfSlabRows) * (size_t)n_grid * 2 * sizeof(uint32_t);
+}
+
+// slabs being consumed at any time ~ pairs / m_tiles; production wants a few more to run ahead
+void fused_ring_depths(int64_t C, int64_t K, int64_t T, int n_grid, int* ring_min, int* ring_pref) {
+  (void)K;
+  const int64_t n_slabs = ceil_div(C, kfSlabRows) * n_grid;
+  const int64_t mp_tiles = ceil_div(T, 256);
+  const int64_t in_flight = ceil_div(74, mp_tiles) + 1;       // 148 SMs -> 74 pairs
+  *ring_min = (int)std::min<int64_t>(n_slabs, in_flight + 2);
+  *ring_pref = (int)std::min<int64_t>(n_slabs, in_flight + 14);
+}
+
+template <typename WT, int G, int BITS>
+static int launch_fused_t(const CUtensorMap& map_x, const CUtensorMap& map_ring, const WT* w, const float* s_grid,
+                          __nv_bfloat16* ring_base, int64_t C, int K, int n_grid, int mp_tiles, int n_tiles,
+                          int k_blocks, int ring, bool sym, uint32_t* ready, uint32_t* done, double* err,
+                          cudaStream_t st) {
+  auto kernel = search_fused_kernel<WT, G, BITS>;
+  const size_t smem = (size_t)kfStages * kfStageBytes + 1024 + 256;
+  AWQK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0;
+  AWQK_CUDA(cudaGetDevice(&dev));
+  AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t total = (int64_t)n_tiles * n_grid * mp_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kfThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(sms / 2) * 2, 1, 1);
+  int max_clusters = 0;
+  AWQK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+  const int64_t pairs = std::min<int64_t>(std::min<int64_t>(total, sms / 2), max_clusters);
+  if (pairs <= 0) return AWQK_E_NODEVICE;
+  cfg.gridDim = dim3((unsigned)pairs * 2, 1, 1);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;                 // all CTAs resident: they wait on one another
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int sym_i = sym ? 1 : 0;
+  AWQK_CUDA(cudaLaunchKernelEx(&cfg, kernel, map_x, map_ring, w, s_grid, ring_base, C, K, n_grid, mp_tiles, n_tiles,
+                               k_blocks, ring, sym_i, ready, done, err));
+  return AWQK_OK;
+}
+
+int launch_search_fused(const void* w, int dtype, int64_t C, int64_t K, const void* x_bf16, int64_t T,
+                        const float* s_grid, int n_grid, int g, int bits, bool sym, double* err_sum, void* sync,
+                        void* ring_base, int ring, cudaStream_t st) {
+  if (tensor_map_encoder() == nullptr) return AWQK_E_NODEVICE;
+  if (ring <= 0) return AWQK_E_WORKSPACE;
+  const int n_tiles = (int)ceil_div(C, kfSlabRows), mp_tiles = (int)ceil_div(T, 256), k_blocks = (int)ceil_div(K, kfBK);
+  const int64_t n_slabs = (int64_t)n_tiles * n_grid;
+  if (n_slabs * mp_tiles > 0x7FFFFFFF) return AWQK_E_BADARG;
+  ring = (int)std::min<int64_t>(ring, n_slabs);
+  CUtensorMap map_x, map_ring;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)T};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    if (!encode_bf16_sw128(&map_x, x_bf16, 2, dims, strides, kfBM)) return AWQK_E_BADARG;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)kfSlabRows, (cuuint64_t)ring};
+    const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)kfSlabRows * (cuuint64_t)K * 2};
+    if (!encode_bf16_sw128(&map_ring, ring_base, 3, dims, strides, kfBNh)) return AWQK_E_BADARG;
+  }
+  uint32_t* ready = reinterpret_cast<uint32_t*>(sync);
+  uint32_t* done = ready + n_slabs;
+  AWQK_CUDA(cudaMemsetAsync(sync, 0, (size_t)n_slabs * 2 * sizeof(uint32_t), st));
+  auto* ring_bf = reinterpret_cast<__nv_bfloat16*>(ring_base);
+#define AWQK_FUSED(WT, GG, BB)                                                                                      \
+  return launch_fused_t<WT, GG, BB>(map_x, map_ring, reinterpret_cast<const WT*>(w), s_grid, ring_bf, C, (int)K,  \
+                                    n_grid, mp_tiles, n_tiles, k_blocks, ring, sym, ready, done, err_sum, st)
+#define AWQK_FUSED_G(WT, BB)                                  \
+  do {                                                        \
+    if (g == 32) AWQK_FUSED(WT, 32, BB);                      \
+    if (g == 64) AWQK_FUSED(WT, 64, BB);                      \
+    AWQK_FUSED(WT, 128, BB);                                  \
+  } while (0)
+  if (dtype == AWQK_BF16) { if (bits == 4) AWQK_FUSED_G(__nv_bfloat16, 4); else AWQK_FUSED_G(__nv_bfloat16, 8); }
+  if (dtype == AWQK_FP16) { if (bits == 4) AWQK_FUSED_G(__half, 4); else AWQK_FUSED_G(__half, 8); }
+  if (dtype == AWQK_FP32) { if (bits == 4) AWQK_FUSED_G(float, 4); else AWQK_FUSED_G(float, 8); }
+#undef AWQK_FUSED_G
+#undef AWQK_FUSED
+  return AWQK_E_UNSUPPORTED;
+}
+
+}  // namespace awqk

@@ -12,12 +12,11 @@
 //     empty[s]  one per CTA, released by the leader's tcgen05.commit.cta_group::2 multicast
 //     tfull[a]  one per CTA (accumulator ready), multicast commit
 //     tempty[a] leader only, count 8: the 4 epilogue warps of both CTAs arrive (remote arrive from CTA 1)
-#include <cuda.h>
-
 #include <algorithm>
 #include <atomic>
 
-#include "awqk_common.cuh"
+#include "awqk_search.cuh"
+#include "awqk_tc.cuh"
 
 namespace awqk {
 
@@ -28,91 +27,6 @@ constexpr int k2BBytes = k2BNh * k2BK * 2;   // 16 KiB
 constexpr int k2StageBytes = k2ABytes + k2BBytes;
 constexpr int k2Threads = 192;
 constexpr uint32_t k2TmemCols = 512;
-constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (pair clusters)
-
-__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mb_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mb_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mb_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(1000000u)
-        : "memory");
-  } while (!ok);
-}
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mb_arrive_cluster(uint32_t local_bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar),
-      "r"(rank)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
-      : "memory");
-}
-__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                             uint32_t leader_bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-          dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar)
-      : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr) {
-  const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-  return ((uint64_t)hi << 32) | lo;
-}
-// kind::f16: D = F32, A = B = BF16, K-major both, N = 256, M = 256 (pair)
-constexpr uint32_t k2Idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k2BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(k2Idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {   // arrive on `bar` in both CTAs of the pair
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"((uint16_t)3)
-      : "memory");
-}
-__device__ __forceinline__ void tm_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 sqerr_gemm2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dw,
@@ -246,42 +160,20 @@ sqerr_gemm2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
   }
 }
 
-typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// returns AWQK_OK, or an error; caller falls back to nothing (errors are reported)
+// returns AWQK_OK, or an error code
 int launch_sqerr_gemm2(const void* x_bf16, const void* dw_bf16, int64_t T, int64_t C, int64_t K, int n_s, double* err,
                        cudaStream_t st) {
-  static EncodeTiledFn2 encode = []() -> EncodeTiledFn2 {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn2>(p);
-  }();
-  if (encode == nullptr) return AWQK_E_NODEVICE;
+  if (tensor_map_encoder() == nullptr) return AWQK_E_NODEVICE;
   CUtensorMap map_x, map_dw;
   {
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)T};
     const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    const cuuint32_t box[2] = {k2BK, k2BM};
-    const cuuint32_t estr[2] = {1, 1};
-    if (encode(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x_bf16), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return AWQK_E_BADARG;
+    if (!encode_bf16_sw128(&map_x, x_bf16, 2, dims, strides, k2BM)) return AWQK_E_BADARG;
   }
   {
     const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)C, (cuuint64_t)n_s};
     const cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)C * (cuuint64_t)K * 2};
-    const cuuint32_t box[3] = {k2BK, k2BNh, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (encode(&map_dw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(dw_bf16), dims, strides, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return AWQK_E_BADARG;
+    if (!encode_bf16_sw128(&map_dw, dw_bf16, 3, dims, strides, k2BNh)) return AWQK_E_BADARG;
   }
   const int mp_tiles = (int)ceil_div(T, 256), n_tiles = (int)ceil_div(C, k2BN), k_blocks = (int)ceil_div(K, k2BK);
   const int64_t total = (int64_t)n_s * mp_tiles * n_tiles;

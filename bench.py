@@ -3,32 +3,37 @@
 
     "quantize+pack GB/s of BF16 weights; end-to-end s/model at 1/2/4/8 B200"
 
-One *step* = one pass of the hot path (int4, g=128 group quantization + nibble pack + packed zero
-points + fp16 scales) over every tensor of the workload.  N=1 workload = BASELINE.json configs[1]
-(OPT-350m-shaped full convert, synthetic random-init bf16 weights).  With N>1 (torchrun) every
-rank owns its LPT share of N model replicas' tensors (weak scaling, no data-path collective; NCCL
-only for the barrier / max-over-ranks timing and the final metadata gather).
+One *step* = one full AWQ conversion of the workload's tensors that this job owns: for every nn.Linear weight the
+20-point activation-aware alpha search (column statistic -> scale grid -> fused fake-quant producer + tcgen05 GEMM
+scores -> device argmin) and the final column-scaled int4 g128 group quantization + nibble pack + packed zeros +
+fp16 scales; for every other tensor the plain group quantization + pack.  All of it is inside `value`.
 
-  value      whole-job GB/s of BF16 weights, inputs resident in HBM, CUDA-event timed
-  e2e        same metric through the public API (AWQQuantizer.quantize_model(arena, pack=True)):
-             pinned host arena -> chunked H2D -> K1 -> D2H of the packed results, inside the timed region
-  roofline   the dominant kernel (K1 group_quant_tma) against the measured HBM peak
-  cpu_baseline  the reference's algorithm on the host cores (oracle port; bounded sample)
-  search     (when built) the activation-aware alpha search leg: s/model and tensor roofline
+Workloads (BASELINE.json configs):  --gpus 1 -> Llama-3-8B shape (configs[2]); --gpus 2/4/8 -> Llama-3-70B shape
+(configs[3]) partitioned over the ranks by tensor (LPT, the reference's own never-called partition_tensors,
+main.py:395-427) with NO data-path collective -- strong scaling over 2/4/8.  `--workload` overrides.
 
-`--impl reference` times the reference's own CPU implementation of the path (the group-at-a-time
-port of awq.py:332-368 in oracle/awq_oracle.py -- the reference is pure Python and cannot travel to
-the GPU box) on a bounded sample per step.
+  value        whole-job GB/s of BF16 weights (model bytes / max-over-ranks step time), inputs resident in HBM,
+               CUDA events around >= 1 s of back-to-back steps
+  e2e          the same conversion through the call a user makes -- AWQQuantizer.quantize_model(dict of ordinary
+               (pageable) host tensors, activations=..., pack=True) -- host->device and device->host inside
+  roofline     the dominant kernel (search_fused_kernel: tensor-core bound) against the measured bf16 peak
+  pack         the K1 launches of the same model alone (HBM bound): burst and sustained, against the measured HBM peak
+  cpu_baseline the reference's own Python loop (oracle/_ref when vendored by build(), else the oracle port) on a
+               bounded sample, host cores stated
+
+`--impl reference` times the reference's CPU implementation of the path on a bounded sample per step.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "awq-converter_b200")):
@@ -42,18 +47,25 @@ UNIT = "GB/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="opt-350m")
+    ap.add_argument("--workload", default="auto", help="auto: llama3-8b on 1 GPU, llama3-70b on 2/4/8")
     ap.add_argument("--group-size", type=int, default=128)
-    ap.add_argument("--arith", default="native", choices=["native", "fp32"])
     ap.add_argument("--symmetric", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-search", action="store_true", help="plain quantize+pack of every tensor (no activations)")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--search-tokens", type=int, default=2048)
+    ap.add_argument("--n-grid", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
+
+
+def pick_workload(args, world):
+    if args.workload != "auto":
+        return args.workload
+    return "llama3-8b" if world == 1 else "llama3-70b"
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -62,15 +74,17 @@ def measured_peaks():
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "measured"
-    return 6650.0, 1590.0, "fallback"
+        sus = float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)))
+        return {"hbm": float(d["hbm_gbs"]), "tf_sustained": sus, "tf_burst": float(d.get("bf16_tflops_burst", sus)),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tf_sustained": 1590.0, "tf_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md)."""
 
-    def __init__(self, index: int):
-        self.index = index
+    def __init__(self, index: int, period_ms: int = 200):
+        self.index, self.period_ms = index, period_ms
         self.rows = []
         self.proc = None
 
@@ -80,7 +94,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -93,79 +107,124 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        pw = sorted(float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
         busy = [v for v in sm if v > 0.6 * (mx[0] if mx else 1)] or sm
         return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": reasons, "samples": len(sm)}
-
-
-def synth_weight_device(name, shape, dev, torch):
-    import zlib
-    g = torch.Generator(device=dev)
-    g.manual_seed(zlib.crc32(name.encode()) ^ 0xA11CE)
-    return (torch.randn(shape, generator=g, device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+                "reasons": reasons, "samples": len(sm), "power_w_median": pw[len(pw) // 2] if pw else None}
 
 
 def bytes_per_elem(g):
     return 2.0 + 0.5 + 2.0 / g + 0.5 / g      # bf16 in + nibble + fp16 scale/g + 4-bit zero/g
 
 
-# ----------------------------------------------------------------------------- reference arm
-def loop_port_rate(torch, O, w, sym, g, seconds):
-    """runs the group-at-a-time port on as many leading rows of `w` as fit in `seconds`"""
-    rows = w.shape[0]
-    t0 = time.perf_counter()
-    O.group_quant_loop(w[:2].contiguous(), 4, g, sym, True)            # calibration (also warms torch)
-    per_row = (time.perf_counter() - t0) / 2
-    take = max(2, min(rows, int(seconds / max(per_row, 1e-6))))
-    sample = w[:take].contiguous()
-    t0 = time.perf_counter()
-    O.group_quant_loop(sample, 4, g, sym, True)
-    dt = time.perf_counter() - t0
-    return sample.numel() * 2 / dt / 1e9, take, dt
+def seed_of(name: str) -> int:
+    return zlib.crc32(name.encode()) ^ 0xA11CE
+
+
+# ----------------------------------------------------------------------------- the reference on the host cores
+def load_reference_quantizer():
+    """the UNMODIFIED reference package, vendored by __graft_entry__.build() into the git-ignored oracle/_ref/
+    (it travels to the GPU box with the snapshot; /root/reference does not exist there).  None when absent."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "awq_quantizer")):
+        return None
+    import importlib.util
+    path = os.path.join(ref_dir, "awq_quantizer", "quantization", "awq.py")
+    # loaded under a private name so that it can never shadow the product package `awq_quantizer`
+    import types
+    pkg_names = ["_awq_ref", "_awq_ref.utils", "_awq_ref.quantization"]
+    for nm in pkg_names:
+        if nm not in sys.modules:
+            m = types.ModuleType(nm)
+            m.__path__ = [os.path.join(ref_dir, "awq_quantizer", *nm.split(".")[1:])]
+            sys.modules[nm] = m
+    try:
+        for sub in ("utils.logger", "utils.tensor_utils", "quantization.awq"):
+            nm = "_awq_ref." + sub
+            if nm in sys.modules:
+                continue
+            spec = importlib.util.spec_from_file_location(nm, os.path.join(ref_dir, "awq_quantizer", *sub.split(".")) + ".py")
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[nm] = mod
+            spec.loader.exec_module(mod)
+        return sys.modules["_awq_ref.quantization.awq"].AWQQuantizer
+    except Exception as e:                       # an unexpected reference layout: report the port instead
+        sys.stderr.write(f"[bench] vendored reference not importable ({e}); using the oracle port\n")
+        return None
+
+
+class CpuReference:
+    """quantize(w) of the reference on the host cores: the real class when vendored, else the group-at-a-time port"""
+
+    def __init__(self, g, sym):
+        import torch
+        self.torch, self.g, self.sym = torch, g, sym
+        cls = load_reference_quantizer()
+        if cls is not None:
+            self.kind = "reference"
+            self.qz = cls(bits=4, group_size=g, symmetric=sym, device="cpu", logger_level="ERROR")
+            self.what = "unmodified AWQQuantizer(device='cpu').quantize (awq.py:376) from oracle/_ref"
+        else:
+            from oracle import awq_oracle as O
+            self.kind, self.O = "port", O
+            self.what = "group-at-a-time port of awq.py:332-368 (oracle/awq_oracle.py::group_quant_loop)"
+
+    def run(self, w):
+        if self.kind == "reference":
+            return self.qz.quantize(w)
+        return self.O.group_quant_loop(w, 4, self.g, self.sym, True)
+
+    def rows_for(self, w, seconds):
+        t0 = time.perf_counter()
+        self.run(w[:2].contiguous())
+        per_row = (time.perf_counter() - t0) / 2
+        return max(2, min(w.shape[0], int(seconds / max(per_row, 1e-6))))
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle loop port), all host
-    threads torch will use; each step = a bounded sample of the workload."""
+    """--impl reference: the reference's CPU implementation of the path, all host threads torch will use; each step
+    = a bounded sample (leading rows of the workload's most common linear shape).  The reference has no scale
+    search: its step is the group quantization alone -- less work than the native arm's."""
     import torch
     from awq_quantizer import model_shapes as M
-    from oracle import awq_oracle as O
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
-    specs = [s for s in M.workload(args.workload) if M.numel(s[1]) >= args.group_size]
-    name, shape, _ = max(specs, key=lambda s: M.numel(s[1]) if len(s[1]) == 2 else 0)
+    workload = pick_workload(args, world)
+    specs = [s for s in M.workload(workload) if len(s[1]) == 2 and s[2] is not None]
+    name, shape, _ = max(specs, key=lambda s: M.numel(s[1]))
     torch.manual_seed(0)
     K = shape[1]
+    ref = CpuReference(args.group_size, args.symmetric)
     budget = 150.0 / max(1, args.steps + args.warmup)                   # whole run within a few minutes
-    w = (torch.randn((4096, K)) * 0.02).to(torch.bfloat16)
-    t0 = time.perf_counter()
-    O.group_quant_loop(w[:2].contiguous(), 4, args.group_size, args.symmetric, True)
-    per_row = (time.perf_counter() - t0) / 2
-    rows = max(2, min(4096, int(budget / max(per_row, 1e-6))))
+    w = (torch.randn((min(shape[0], 2048), K)) * 0.02).to(torch.bfloat16)
+    rows = ref.rows_for(w, budget)
     sample = w[:rows].contiguous()
     for _ in range(args.warmup):
-        O.group_quant_loop(sample, 4, args.group_size, args.symmetric, True)
+        ref.run(sample)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.group_quant_loop(sample, 4, args.group_size, args.symmetric, True)
+        ref.run(sample)
     dt = (time.perf_counter() - t0) / args.steps
     val = sample.numel() * 2 / dt / 1e9
-    sample_desc = (f"{rows} rows x {K} of a {args.workload}-shaped bf16 linear per step "
-                   f"({sample.numel() // args.group_size} groups), group-at-a-time port of awq.py:332-368")
+    sample_desc = (f"{rows} rows x {K} of {name.split('.')[-2]} {tuple(shape)} of the {workload} shape per step "
+                   f"({sample.numel() // args.group_size} groups); {ref.what}")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (reference arithmetic dtype)", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-shaped, int4 g{args.group_size} "
-                               f"{'symmetric' if args.symmetric else 'asymmetric'}", "sample": sample_desc},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16 (reference arithmetic dtype)",
+        "data": "synthetic",
+        "config": {"workload": f"{workload}-shaped, int4 g{args.group_size} "
+                               f"{'symmetric' if args.symmetric else 'asymmetric'}", "sample": sample_desc,
+                   "note": "group quantization only: the reference has no activation-aware search to time"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
                          "sample": sample_desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -175,99 +234,133 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- native arm
+class DeviceModel:
+    """This rank's shard of the workload, resident in HBM, and the launch sequences of one conversion."""
+
+    def __init__(self, torch, N, M, shard, dev, *, g, sym, T, n_grid, search):
+        self.torch, self.N, self.L, self.dev = torch, N, N.lib(), dev
+        self.g, self.sym, self.T, self.n_grid = g, sym, T, n_grid
+        gen = torch.Generator(device=dev)
+        self.items = []          # (name, C, K, calib key or None)
+        self.w, self.out, self.x, self.grid = {}, {}, {}, {}
+        ws_bytes = 256
+        for name, shape, ck in shard:
+            C = shape[0] if len(shape) > 1 else 1
+            K = M.numel(shape) // C
+            G = -(-K // g)
+            gen.manual_seed(seed_of(name))
+            self.w[name] = (torch.randn(shape, generator=gen, device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+            packed_zeros_in_kernel = (G % 8 == 0) or G in (1, 2, 4)
+            self.out[name] = {"qweight": torch.empty((C, -(-K // 8)), dtype=torch.int32, device=dev),
+                              "scales": torch.empty((C, G), dtype=torch.float16, device=dev),
+                              "zero_points": None if packed_zeros_in_kernel else torch.empty((C, G), dtype=torch.int32, device=dev),
+                              "qzeros": torch.empty((C, -(-G // 8)), dtype=torch.int32, device=dev)}
+            ck = ck if (search and ck is not None and len(shape) == 2) else None
+            self.items.append((name, C, K, ck))
+            if ck is not None:
+                key = (ck, K)
+                if key not in self.x:
+                    gen.manual_seed(seed_of(f"x/{ck}/{K}"))
+                    gain = torch.exp(torch.randn(K, generator=gen, device=dev))
+                    self.x[key] = (torch.randn((T, K), generator=gen, device=dev) * gain).to(torch.bfloat16)
+                    self.grid[key] = (torch.empty(K, dtype=torch.float64, device=dev),
+                                      torch.empty((n_grid, K), dtype=torch.float32, device=dev),
+                                      torch.empty(2 * n_grid, dtype=torch.float32, device=dev))
+                import ctypes
+                ws_bytes = max(ws_bytes, int(self.L.awqk_workspace_bytes(C, K, T, n_grid, 1, ctypes.byref(ctypes.c_size_t(0)))))
+        self.searched = [it for it in self.items if it[3] is not None]
+        self.plain = [it for it in self.items if it[3] is None]
+        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        self.sel = {n: (torch.empty(n_grid, dtype=torch.float64, device=dev), torch.empty((), dtype=torch.int32, device=dev),
+                        torch.empty(K, dtype=torch.float32, device=dev)) for n, _, K, _ in self.searched}
+        self.elems = sum(C * K for _, C, K, _ in self.items)
+        self.search_flops = sum(2.0 * T * C * K * n_grid for _, C, K, _ in self.searched)
+        # kernels of ours per conversion: grids (colsum + 3 alpha-grid kernels), per linear fused scores + select + K1,
+        # per plain tensor K1 (+ the row-wise zero packer where zero words are not written by K1 itself)
+        self.launches = 4 * len(self.x) + 3 * len(self.searched) + sum(1 if self.out[n]["zero_points"] is None else 2
+                                                                        for n, *_ in self.plain)
+
+    def _st(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def grids(self):
+        N, L, st = self.N, self.L, self._st()
+        for key, x in self.x.items():
+            colsum, s_grid, mnmx = self.grid[key]
+            colsum.zero_()
+            N.check(L.awqk_abs_colsum(x.data_ptr(), N.BF16, x.shape[0], x.shape[1], colsum.data_ptr(), st), "awqk_abs_colsum")
+            N.check(L.awqk_alpha_grid(colsum.data_ptr(), x.shape[0], x.shape[1], self.n_grid, s_grid.data_ptr(),
+                                      mnmx.data_ptr(), st), "awqk_alpha_grid")
+
+    def search(self, final: bool):
+        """awqk_scale_search per linear: scores + argmin + winning scales (+ the final column-scaled K1 pass)"""
+        N, L, st = self.N, self.L, self._st()
+        ws = self.workspace
+        for name, C, K, ck in self.searched:
+            x = self.x[(ck, K)]
+            s_grid = self.grid[(ck, K)][1]
+            err, best, s_best = self.sel[name]
+            o = self.out[name]
+            N.check(L.awqk_scale_search(
+                self.w[name].data_ptr(), N.BF16, C, K, x.data_ptr(), self.T, s_grid.data_ptr(), self.n_grid, self.g, 4,
+                int(self.sym), err.data_ptr(), best.data_ptr(), s_best.data_ptr(), None,
+                o["qweight"].data_ptr() if final else None, o["scales"].data_ptr() if final else None,
+                N.ptr(o["zero_points"]) if final else None, o["qzeros"].data_ptr() if final else None,
+                ws.data_ptr(), ws.numel(), st), "awqk_scale_search")
+
+    def k1(self, items, scaled: bool):
+        N, L, st = self.N, self.L, self._st()
+        for name, C, K, _ in items:
+            o = self.out[name]
+            N.check(L.awqk_group_quant(self.w[name].data_ptr(), N.BF16, C, K, self.g, 4, int(self.sym),
+                                       N.ARITH_FP32 if scaled else N.ARITH_NATIVE, None, o["qweight"].data_ptr(),
+                                       o["scales"].data_ptr(), N.ptr(o["zero_points"]), o["qzeros"].data_ptr(),
+                                       self.sel[name][2].data_ptr() if scaled else None, st), "awqk_group_quant")
+
+    def convert(self):                       # ONE step
+        self.grids()
+        self.search(final=True)
+        self.k1(self.plain, scaled=False)
+
+    def scores_only(self):                   # the dominant kernel's launches alone (roofline)
+        self.search(final=False)
+
+    def pack_only(self):                     # every K1 launch of the conversion alone (HBM roofline)
+        self.k1(self.searched, scaled=True)
+        self.k1(self.plain, scaled=False)
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
     from awq_quantizer import _native as N
     from awq_quantizer import model_shapes as M
+    from awq_quantizer import parallel
     from awq_quantizer.quantization import AWQQuantizer
-    from awq_quantizer.quantization.arena import HostArena, arena_eligible
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    from awq_quantizer import parallel
     numa_node = parallel.bind_to_gpu_numa(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    L = N.lib()
-    g, bits, sym = args.group_size, 4, args.symmetric
-    per = 32 // bits
-    hbm_peak, tf_peak, peak_kind = measured_peaks()
+    g, sym, T, n_grid = args.group_size, args.symmetric, args.search_tokens, args.n_grid
+    search = not args.no_search
+    peaks = measured_peaks()
+    workload = pick_workload(args, world)
 
-    # ---- this rank's share: LPT partition of `world` replicas of the workload (weak scaling) ----
-    specs = M.workload(args.workload)
-    pool = [(f"r{r}/{name}", shape) for r in range(world) for name, shape, _ in specs]
-    bins = M.partition_lpt([(n, M.numel(s) * 2) for n, s in pool], world)
-    mine = set(bins[rank])
-    shapes = {n: s for n, s in pool if n in mine}
-    flat = {n: s for n, s in shapes.items() if arena_eligible(s, torch.bfloat16, g, bits)}
-    single = {n: s for n, s in shapes.items() if n not in flat and M.numel(s) >= 128}   # CLI drops numel < 128 (main.py:250)
-    payload_elems = sum(M.numel(s) for s in flat.values()) + sum(M.numel(s) for s in single.values())
-    payload_bytes = 2 * payload_elems
-
-    # ---- synthetic inputs: generated on the device, one D2H into the pinned host arena (untimed) ----
-    arena = HostArena({n: (tuple(s), torch.bfloat16) for n, s in flat.items()})
-    d_arena = torch.zeros_like(arena.buffers[torch.bfloat16], device=dev)
-    for name, off, n in arena.layout[torch.bfloat16]:
-        d_arena[off:off + n] = synth_weight_device(name, flat[name], dev, torch).reshape(-1)
-    arena.buffers[torch.bfloat16].copy_(d_arena)
-    d_single = {n: synth_weight_device(n, s, dev, torch) for n, s in single.items()}
-    h_single = {n: t.cpu().pin_memory() for n, t in d_single.items()}
-    n_arena = d_arena.numel()
-
-    # ---- device-resident leg ----------------------------------------------------------------------
-    d_q = torch.empty(n_arena // per, dtype=torch.int32, device=dev)
-    d_s = torch.empty(n_arena // g, dtype=torch.float16, device=dev)
-    d_zq = torch.empty(n_arena // g // per, dtype=torch.int32, device=dev)
-    single_out = {}
-    for n, t in d_single.items():
-        C = t.shape[0] if t.dim() > 1 else 1
-        K = t.numel() // C
-        G = -(-K // g)
-        single_out[n] = (C, K, torch.empty((C, -(-K // per)), dtype=torch.int32, device=dev),
-                         torch.empty((C, G), dtype=torch.float16, device=dev),
-                         torch.empty((C, G), dtype=torch.int32, device=dev),
-                         torch.empty((C, -(-G // per)), dtype=torch.int32, device=dev))
-    arith = N.ARITH_FP32 if args.arith == "fp32" else N.ARITH_NATIVE
-    # a row-mode tensor is one K1 launch when its rows are 1 / 2 / 4 groups (zero words packed in the kernel),
-    # else K1 + pack_zeros_rows
-    launches_per_step = 1 + sum(1 if (bits == 4 and v[1] // g in (1, 2, 4)) else 2 for v in single_out.values())
-
-    def k1_arena():
-        st = torch.cuda.current_stream(dev).cuda_stream
-        N.check(L.awqk_group_quant(d_arena.data_ptr(), N.BF16, 1, n_arena, g, bits, int(sym), arith, None,
-                                   d_q.data_ptr(), d_s.data_ptr(), None, d_zq.data_ptr(), None, st))
-
-    def step_launches():
-        # the (small) row-mode tensors first, then the arena: one stream, no fork / join.  (A forked stream
-        # buys nothing: the persistent arena kernel fills every SM, so the small kernels would only run at its tail.)
-        st = torch.cuda.current_stream(dev).cuda_stream
-        for n, t in d_single.items():
-            C, K, qw, sc, zp, zq = single_out[n]
-            N.check(L.awqk_group_quant(t.data_ptr(), N.BF16, C, K, g, bits, int(sym), arith, None, qw.data_ptr(),
-                                       sc.data_ptr(), None if (bits == 4 and K // g in (1, 2, 4)) else zp.data_ptr(), zq.data_ptr(), None, st))
-        k1_arena()
-
-    # one pass = one CUDA graph launch (the per-tensor launches are captured once, replayed per step)
-    step_device, graph_mode = step_launches, "direct launches"
-    try:
-        step_launches()
-        torch.cuda.synchronize(dev)
-        side = torch.cuda.Stream(dev)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            step_launches()
-        graph.replay()
-        torch.cuda.synchronize(dev)
-        step_device, graph_mode = graph.replay, "CUDA graph replay"
-    except Exception as e:      # capture is an optimisation of the launch path only
-        graph_mode = f"direct launches (graph capture failed: {str(e)[:80]})"
-        torch.cuda.synchronize(dev)
+    # ---- this rank's share: LPT by cost (C*K*T for searched linears, bytes otherwise), no data-path collective ----
+    specs = [(n, s, ck) for n, s, ck in M.workload(workload) if M.numel(s) >= 128]      # CLI drops numel < 128 (main.py:250)
+    cost = [(n, M.numel(s) * (T if (search and ck is not None and len(s) == 2) else 2)) for n, s, ck in specs]
+    mine = set(M.partition_lpt(cost, world)[rank])
+    shard = [(n, s, ck) for n, s, ck in specs if n in mine]
+    model = DeviceModel(torch, N, M, shard, dev, g=g, sym=sym, T=T, n_grid=n_grid, search=search)
+    payload_bytes = 2 * model.elems
+    total_bytes = 2 * sum(M.numel(s) for _, s, _ in specs)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -275,7 +368,15 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def timed(fn, steps, warmup):
+        """(max-over-ranks ms per step, this rank's ms per step)"""
         for _ in range(warmup):
             fn()
         barrier()
@@ -285,152 +386,171 @@ def run_native(args):
             fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps
+        mine_ms = e0.elapsed_time(e1) / steps
+        return allmax(mine_ms), mine_ms
 
     clocks = ClockSampler(local)
     clocks.start()
-    ms_step = timed(step_device, args.steps, max(3, args.warmup))
-    ms_k1 = timed(k1_arena, args.steps, 3)                       # the dominant kernel alone (roofline)
-    # (the clock sampler keeps running through the e2e and search legs: all of them are timed regions)
 
-    total_payload = payload_bytes
-    if world > 1:
-        t = torch.tensor([payload_bytes], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        total_payload = float(t.item())
-    value = total_payload / (ms_step * 1e-3) / 1e9
+    # ---- device-resident leg: K whole conversions back to back ------------------------------------------------
+    warm = max(3, args.warmup)
+    ms_step, ms_step_mine = timed(model.convert, args.steps, warm)
+    value = total_bytes / (ms_step * 1e-3) / 1e9
+    timed_region_s = ms_step * args.steps * 1e-3
 
-    arena_payload_elems = sum(M.numel(s) for s in flat.values())
-    achieved = bytes_per_elem(g) * arena_payload_elems / (ms_k1 * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
-    if os.path.exists(tpath):
+    # ---- dominant kernel: the fused score kernel, same launches as in the step, alone, back to back (sustained) ----
+    roofline = None
+    if model.searched:
+        model.grids()
+        ms_scores, _ = timed(model.scores_only, max(1, min(args.steps, 3)), 1)
+        flops = model.search_flops
+        achieved = flops / (ms_scores * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "search_fused_kernel (fake-quant producer warps + tcgen05 cta_group::2 GEMM)",
+                    "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
+                    "frac_of_burst_peak": achieved / peaks["tf_burst"], "traffic": None, "peak_source": peaks["source"],
+                    "peak_kind": "sustained (kernel timed inside %.2f s of back-to-back launches)" % (ms_scores * 1e-3),
+                    "launches": len(model.searched), "us_per_launch": ms_scores * 1e3 / len(model.searched),
+                    "algorithmic_flops_per_launch": flops / len(model.searched),
+                    "flops_formula": "2*T*C*K*n_grid (delta form; SURVEY's 2*T*C*K*(n_grid+1) gives %.1f TFLOP/s)"
+                                     % (achieved * (n_grid + 1) / n_grid),
+                    "share_of_step": ms_scores / ms_step_mine}
+
+    # ---- pack kernels alone (HBM bound): one pass = burst, >= 1 s back to back = sustained ---------------------
+    alg_bytes = bytes_per_elem(g) * model.elems
+    burst = []
+    for _ in range(5):
+        ms, _ = timed(model.pack_only, 1, 1)
+        burst.append(ms)
+    ms_burst = min(burst)
+    reps = max(3, int(1200.0 / max(ms_burst, 1e-3)))
+    ms_sus, _ = timed(model.pack_only, reps, 0)
+    pack = {"bound": "hbm", "kernel": "group_quant_tma (K1: column-slab mode for searched linears, flat mode otherwise)",
+            "achieved": alg_bytes / (ms_sus * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+            "frac": alg_bytes / (ms_sus * 1e-3) / 1e9 / peaks["hbm"], "peak_source": peaks["source"],
+            "sustained": {"ms_per_pass": ms_sus, "passes": reps, "gbs_of_bf16": payload_bytes / (ms_sus * 1e-3) / 1e9},
+            "burst": {"ms_per_pass": ms_burst, "achieved": alg_bytes / (ms_burst * 1e-3) / 1e9,
+                      "frac": alg_bytes / (ms_burst * 1e-3) / 1e9 / peaks["hbm"],
+                      "gbs_of_bf16": payload_bytes / (ms_burst * 1e-3) / 1e9},
+            "algorithmic_bytes_per_pass": alg_bytes, "traffic": None, "share_of_step": ms_burst / ms_step_mine}
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath):                      # per-launch DRAM bytes from the committed ncu --set full captures
         with open(tpath) as f:
             tj = json.load(f)
-        traffic = tj.get(f"{args.workload}/g{g}/{args.arith}")
-    roofline = {"bound": "hbm", "kernel": "group_quant_tma (K1 v2)", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
-                "us_per_launch": ms_k1 * 1e3, "algorithmic_bytes_per_launch": bytes_per_elem(g) * arena_payload_elems}
+        if roofline is not None:
+            roofline["traffic"] = tj.get("search_fused_kernel")
+        pack["traffic"] = tj.get("group_quant_tma")
+    if roofline is None:                           # --no-search: the pack kernel is the dominant one
+        roofline = {k: pack[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "traffic", "peak_source")}
 
-    # ---- e2e leg: public API, pinned host arena in, packed host results out --------------------------
-    qz = AWQQuantizer(bits=bits, group_size=g, symmetric=sym, device=f"cuda:{local}", logger_level="ERROR",
-                      arith=args.arith)
-
-    def step_e2e():
-        r = qz.quantize_model(arena, pack=True)
-        r.update(qz.quantize_model(h_single, pack=True))       # rows that are not whole packed-zero words
-        return r
-
-    for _ in range(2):
-        res = step_e2e()
-    barrier()
-    e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = step_e2e()
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
+    per_rank = None
     if world > 1:
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_val = total_payload / (dt / e2e_steps) / 1e9
-    # the unchanged reference call -- quantize_model(dict) -> int32 tensor_q / fp16 scales / int32 zero points --
-    # for the record (D2H of 4 B per element makes it PCIe-bound at ~1/4 of the packed path)
-    host_dict = {n: arena.views[n].clone() for n in flat}      # ordinary pageable tensors, as a loader returns them
-    host_dict.update({n: t.clone() for n, t in h_single.items()})
-    # ... and the packed form of the same call: first call of a fresh quantizer (pageable results through the
-    # native gather pipeline's bounded pinned ring -- what a one-shot conversion sees), then warm calls
-    qz2 = AWQQuantizer(bits=bits, group_size=g, symmetric=sym, device=f"cuda:{local}", logger_level="ERROR",
-                       arith=args.arith)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    qz2.quantize_model(host_dict, pack=True)
-    torch.cuda.synchronize(dev)
-    dt_dict_first = time.perf_counter() - t0
-    qz2.quantize_model(host_dict, pack=True)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for _ in range(3):
-        qz2.quantize_model(host_dict, pack=True)
-    torch.cuda.synchronize(dev)
-    dt_dict_pack = (time.perf_counter() - t0) / 3
-    qz.quantize_model(host_dict)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for _ in range(3):
-        qz.quantize_model(host_dict)
-    torch.cuda.synchronize(dev)
-    dt_ref_layout = (time.perf_counter() - t0) / 3
-    h2d = arena.nbytes() + sum(t.numel() * 2 for t in h_single.values())
-    d2h = (n_arena // per) * 4 + (n_arena // g) * 2 + (n_arena // g // per) * 4
-    d2h += sum(sum(v.numel() * v.element_size() for k, v in res[n].items() if v.dim() > 0) for n in h_single)
+        rows = [None] * world
+        dist.all_gather_object(rows, {"rank": rank, "tensors": len(shard), "searched": len(model.searched),
+                                      "bf16_bytes": payload_bytes, "step_ms": round(ms_step_mine, 3),
+                                      "pack_burst_ms": round(ms_burst, 4), "pack_sustained_ms": round(ms_sus, 4)})
+        per_rank = rows
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.arith == "native" else "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-shaped full convert x{world} (LPT over ranks), int4 g{g} "
-                               f"{'symmetric' if sym else 'asymmetric'}, arith={args.arith}",
-                   "tensors_per_rank": len(shapes), "params_per_rank": payload_elems,
-                   "l2": "inputs larger than L2 (arena %.0f MB per pass)" % (n_arena * 2 / 1e6),
-                   "parallelism": f"tensor-sharded x{world}, no data-path collective", "launch": graph_mode,
-                   "numa_node_rank0": numa_node},
-        "s_per_model": ms_step * 1e-3, "roofline": roofline,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "s_per_model": dt / e2e_steps, "api": "AWQQuantizer.quantize_model(HostArena, pack=True)",
-                "from_pageable_dict": {"value": payload_bytes / dt_dict_pack / 1e9, "unit": UNIT, "s_per_model": dt_dict_pack,
-                                       "first_call_s": dt_dict_first,
-                                       "api": "AWQQuantizer.quantize_model(dict of pageable tensors, pack=True)  (per rank)"},
-                "reference_layout": {"value": payload_bytes / dt_ref_layout / 1e9, "unit": UNIT, "s_per_model": dt_ref_layout,
-                                     "api": "AWQQuantizer.quantize_model(dict)  (unchanged reference call; per rank)"}},
-        "gpu_launches": launches_per_step * args.steps,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "bf16 (tcgen05 bf16 x bf16 -> f32 scores; f32 quantizer arithmetic)", "data": "synthetic",
+        "config": {"workload": f"{workload}-shaped full AWQ convert: {n_grid}-point alpha search (T={T}) + int4 g{g} "
+                               f"{'symmetric' if sym else 'asymmetric'} quantize + pack" if search else
+                               f"{workload}-shaped plain int4 g{g} quantize + pack (no search)",
+                   "tensors": len(specs), "params": total_bytes // 2, "bf16_GB": total_bytes / 1e9,
+                   "searched_linears_this_rank": len(model.searched),
+                   "l2": "inputs larger than L2 (%.1f GB of weights per rank per step)" % (payload_bytes / 1e9),
+                   "parallelism": f"tensor-sharded x{world} (LPT), no data-path collective",
+                   "timed_region_s": timed_region_s, "numa_node_rank0": numa_node, "per_rank": per_rank},
+        "s_per_model": ms_step * 1e-3, "roofline": roofline, "pack": pack,
+        "gpu_launches": model.launches * args.steps,
     }
 
-    # ---- activation-aware search leg (K2), when built ----------------------------------------------
-    if not args.no_search:
-        try:
-            from awq_quantizer.quantization import search as S
-            line["search"] = S.bench_leg(args, dev, world, rank, tf_peak, peak_kind)
-        except ImportError:
-            line["search"] = None
-
+    # ---- e2e leg: the public call, ordinary host tensors in, packed host results out --------------------------
+    if not args.no_e2e:
+        line["e2e"] = e2e_leg(torch, dist, AWQQuantizer, model, dev, world, local, g, sym, n_grid, total_bytes, allmax, barrier)
     line["clocks"] = clocks.stop()
 
-    # ---- CPU baseline: the oracle on this box's host cores (rank 0, N=1 only) -----------------------
+    # ---- CPU baseline: the reference on this box's host cores (rank 0, N=1 only) ------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import awq_oracle as O
-        name, shape = max(flat.items(), key=lambda kv: M.numel(kv[1]) if len(kv[1]) == 2 and kv[1][1] >= 1024 else 0)
-        w = arena.views[name][:4096].clone()
-        gbs, rows, secs = loop_port_rate(torch, O, w, sym, g, args.cpu_seconds)
-        cb = {"value": gbs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-              "sample": f"first {rows} rows of {name.split('/', 1)[1]} {tuple(shape)} bf16, {secs:.1f}s of the "
-                        f"group-at-a-time port (awq.py:332-368)"}
-        try:
-            from oracle import c_oracle as CO
-            big = arena.views[name]
-            t0 = time.perf_counter()
-            CO.group_quant(big, 4, g, sym, threads=os.cpu_count())
-            cb["c_restatement_all_cores"] = {"value": big.numel() * 2 / (time.perf_counter() - t0) / 1e9, "unit": UNIT,
-                                             "cores": os.cpu_count(), "sample": f"{name.split('/', 1)[1]} whole tensor"}
-        except Exception as e:   # C oracle is optional test infrastructure
-            cb["c_restatement_all_cores"] = {"error": str(e)[:100]}
-        line["cpu_baseline"] = cb
+        line["cpu_baseline"] = cpu_baseline(torch, model, g, sym, args.cpu_seconds)
 
     if world > 1:
-        meta = [None] * world
-        dist.all_gather_object(meta, {"rank": rank, "tensors": len(shapes), "bytes": payload_bytes})
-        if rank == 0:
-            line["config"]["per_rank"] = meta
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
     return 0
+
+
+def e2e_leg(torch, dist, AWQQuantizer, model, dev, world, local, g, sym, n_grid, total_bytes, allmax, barrier):
+    """AWQQuantizer.quantize_model(dict of pageable host tensors, activations=..., pack=True): the drop-in call.
+    Every step copies the step's weights and activations host -> device and the packed results device -> host."""
+    import psutil
+    need = 2 * model.elems * 1.6 + (4 << 30)
+    avail = psutil.virtual_memory().available / max(1, world)
+    items = model.items
+    note = None
+    if need > avail:                                     # bounded host memory: a leading slice of the shard
+        frac = max(0.05, avail / need * 0.8)
+        keep, acc = [], 0
+        for it in items:
+            keep.append(it)
+            acc += it[1] * it[2]
+            if acc >= frac * model.elems:
+                break
+        items, note = keep, f"host memory bound: first {len(keep)} of {len(model.items)} tensors of the shard"
+    host_w = {n: model.w[n].cpu() for n, *_ in items}                      # ordinary pageable tensors, as a loader returns
+    host_x = {key: x.cpu().pin_memory() for key, x in model.x.items()}
+    acts = {n: host_x[(ck, K)] for n, _, K, ck in items if ck is not None}
+    elems = sum(C * K for _, C, K, _ in items)
+    qz = AWQQuantizer(bits=4, group_size=g, symmetric=sym, device=f"cuda:{local}", logger_level="ERROR", n_grid=n_grid)
+    times = []
+    res = None
+    for it in range(3):
+        del res
+        barrier()
+        t0 = time.perf_counter()
+        res = qz.quantize_model(host_w, activations=acts or None, pack=True)
+        torch.cuda.synchronize(dev)
+        times.append(time.perf_counter() - t0)
+        assert len(res) == len(host_w), (len(res), len(host_w))
+    dt = allmax(min(times[1:]))
+    first = allmax(times[0])
+    d2h = sum(v.numel() * v.element_size() for r in res.values() for v in r.values() if hasattr(v, "numel") and v.dim() > 0)
+    h2d = 2 * elems + sum(x.numel() * 2 for x in {id(a): a for a in acts.values()}.values())
+    done_bytes = 2 * elems
+    if world > 1:
+        t = torch.tensor([done_bytes, h2d, d2h], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        done_bytes, h2d, d2h = (float(v) for v in t)
+    return {"value": done_bytes / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "s_per_model": dt * (total_bytes / done_bytes), "s_per_step_measured": dt, "first_call_s": first,
+            "steps": len(times) - 1, "api": "AWQQuantizer.quantize_model(dict of pageable host tensors, activations=..., pack=True)",
+            "coverage": note or "the whole shard of every rank"}
+
+
+def cpu_baseline(torch, model, g, sym, seconds):
+    ref = CpuReference(g, sym)
+    name, C, K, _ = max(model.searched or model.items, key=lambda it: it[1] * it[2])
+    w = model.w[name][:2048].cpu()
+    rows = ref.rows_for(w, seconds)
+    sample = w[:rows].contiguous()
+    t0 = time.perf_counter()
+    ref.run(sample)
+    secs = time.perf_counter() - t0
+    cb = {"value": sample.numel() * 2 / secs / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
+          "sample": f"first {rows} rows of {name} ({C}x{K}) bf16, {secs:.1f} s; {ref.what}; group quantization only "
+                    f"(the reference has no scale search)"}
+    try:                                               # the C restatement on all cores, and the oracle's search, for scale
+        from oracle import c_oracle as CO
+        big = model.w[name].cpu()
+        t0 = time.perf_counter()
+        CO.group_quant(big, 4, g, sym, threads=os.cpu_count())
+        cb["c_restatement_all_cores"] = {"value": big.numel() * 2 / (time.perf_counter() - t0) / 1e9, "unit": UNIT,
+                                         "cores": os.cpu_count(), "sample": f"{name} whole tensor"}
+    except Exception as e:
+        cb["c_restatement_all_cores"] = {"error": str(e)[:100]}
+    return cb
 
 
 def main():

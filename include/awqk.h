@@ -12,9 +12,12 @@
  *   - plain pointers and sizes; no torch / C++ types.  Device pointers unless the name says host.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - return value: 0 = ok, negative = AWQK_E_* (awqk_error_string() names it).  No exceptions,
- *     no allocation inside (except awqk_pipe_*, which owns its staging buffers), no global
- *     mutable state: every call is re-entrant and may be issued concurrently from several host
- *     threads (the reference calls quantize() from a ThreadPoolExecutor, main.py:609-621).
+ *     no allocation inside (except awqk_pipe_*, which owns its staging buffers).  Every call is
+ *     re-entrant and may be issued concurrently from several host threads (the reference calls
+ *     quantize() from a ThreadPoolExecutor, main.py:609-621).  The only process-wide state is
+ *     write-once caches (the driver entry point of cuTensorMapEncodeTiled, per-device "opt-in shared
+ *     memory size was set" bits) and the lazily created copy-thread pool of awqk_pipe_*; all are
+ *     initialised thread-safely and never change afterwards.
  *   - the device the pointers live on is made current for the duration of the call.
  */
 #ifndef AWQK_H_
@@ -27,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AWQK_VERSION 100
+#define AWQK_VERSION 200
 
 #if defined(__GNUC__)
 #define AWQK_API __attribute__((visibility("default")))
@@ -106,9 +109,42 @@ AWQK_API int awqk_dequant_packed(const uint32_t* q_packed, const void* scales_f1
 AWQK_API int awqk_bf16_to_fp16(const void* in_bf16, void* out_fp16, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * K2  activation-aware scale search (no reference counterpart; definition = oracle/awq_oracle.py
- *     search_scales).  See DESIGN.md.  Declared in awqk_search section below once built.
+ * K2  activation-aware scale search.  NO reference counterpart: awq.py only cites the AWQ paper
+ *     (awq.py:1-7; scale_method is stored at awq.py:36,66 and never read).  Definition =
+ *     oracle/awq_oracle.py::search_scales, which composes the reference's own group quantizer
+ *     (awq.py:173-250) -- "parity unpinned" for everything but that quantizer.
+ *
+ *       m      = mean_t |X[t,:]|                                   (fp64 accumulation)
+ *       s_i    = clamp(m^(i/n_grid), 1e-4) / sqrt(max*min)          i = 0 .. n_grid-1
+ *       dW_i   = bf16( W - dequant(group_quant(W*s_i)) / s_i )      fp32 arithmetic
+ *       err_i  = mean_{t,c} (X . dW_i^T)^2                          tcgen05 bf16 GEMM, fp32 accumulate in TMEM
+ *       best   = first minimum of err;  final result = group_quant(fp32(W) * s_best)
  * ------------------------------------------------------------------------------------- */
+
+/* The whole search for ONE tensor, queued on `stream` without any host synchronisation:
+ *   w          [C, K] bf16/fp16/fp32;   x_bf16 [T, K] bf16 calibration activations.
+ *   s_grid     nullable fp32 [n_grid, K]: scale vectors to score (e.g. cached per activation tensor with
+ *              awqk_abs_colsum + awqk_alpha_grid).  NULL: computed from x_bf16 inside the workspace.
+ *   err_mean   nullable fp64 [n_grid]: the scores;  best_idx nullable int32[1];  best_s fp32 [K] (required).
+ *   q_unpacked / q_packed / scales_f16 / zp / zp_packed: outputs of the final pass, exactly as in
+ *              awqk_group_quant(..., arith = FP32, col_scale = best_s); scales_f16 == NULL skips the final pass.
+ *   workspace  device memory, 256-byte aligned, >= the minimum of awqk_workspace_bytes (the preferred size
+ *              lets the delta producers run further ahead of the GEMM).  Must not be shared by two searches
+ *              that may run at the same time.
+ *   Requires group_size in {32,64,128}, K % group_size == 0, K % 64 == 0, 16-byte aligned bases.
+ * Inside: the score kernel is ONE persistent launch in which producer warps compute the dW operand of the
+ * tensor-core GEMM tile by tile (awqk_search_fused.cu); the argmin, the winning scale vector and the final
+ * column-scaled K1 pass follow on the same stream. */
+AWQK_API int awqk_scale_search(const void* w, int dtype, int64_t C, int64_t K, const void* x_bf16, int64_t T,
+                      const float* s_grid, int n_grid, int group_size, int bits, int symmetric,
+                      double* err_mean, int32_t* best_idx, float* best_s, int32_t* q_unpacked,
+                      uint32_t* q_packed, void* scales_f16, int32_t* zp, uint32_t* zp_packed,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* preferred workspace size of awqk_scale_search for this problem; *minimum (nullable) gets the smallest
+ * size it accepts.  have_s_grid != 0: the caller passes s_grid.  0 on bad arguments. */
+AWQK_API size_t awqk_workspace_bytes(int64_t C, int64_t K, int64_t T, int n_grid, int have_s_grid, size_t* minimum);
+
+/* ---- the stages of the search as separate calls (tests, tools) ---- */
 
 /* column statistic: sum_t |X[t,k]| accumulated in fp64.  X is [T, K] bf16/fp16/fp32.
  * `colsum` fp64 [K] must be zeroed by the caller (or accumulate over several calls). */
@@ -121,15 +157,14 @@ AWQK_API int awqk_alpha_grid(const double* colsum, int64_t T, int64_t K, int n_g
 
 /* dW[i] = bf16( W - dequant(group_quant(W * s_i)) / s_i ), i = 0..n_s-1; fp32 arithmetic.
  *   w [C,K] bf16/fp16/fp32;  s [n_s, K] fp32;  dw bf16 [n_s, C, K].  K % group_size == 0.
- *   rcp_workspace: nullable, n_s*K floats; when given (and K % 32 == 0) the packed-math kernel runs
- *   (it stores the refined reciprocals of s there); results are identical either way. */
+ * Stand-alone form of the producer inside awqk_scale_search (same device code, bit-identical). */
 AWQK_API int awqk_fakequant_delta(const void* w, int dtype, int64_t C, int64_t K, int group_size, int bits,
-                         int symmetric, const float* s, int n_s, void* dw_bf16, float* rcp_workspace,
-                         void* stream);
+                         int symmetric, const float* s, int n_s, void* dw_bf16, void* stream);
 
 /* err[i] += sum over [T, C] of (X . dW_i^T)^2, tcgen05 bf16 GEMM with fp32 TMEM accumulators and a
  * fused sum-of-squares epilogue.  X [T,K] bf16, dW [n_s, C, K] bf16, err fp64 [n_s] (zeroed by the
- * caller).  Requires K % 64 == 0 and 16-byte aligned bases. */
+ * caller).  Requires K % 8 == 0 and 16-byte aligned bases.  Stand-alone form of the consumer inside
+ * awqk_scale_search. */
 AWQK_API int awqk_sqerr_gemm(const void* x_bf16, const void* dw_bf16, int64_t T, int64_t C, int64_t K,
                     int n_s, double* err, void* stream);
 
