@@ -188,3 +188,46 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     res = json.load(open(out))
     assert res["merged_tensors"] == res["all"] == 194          # every tensor exactly once
     assert abs(res["bytes"][0] - res["bytes"][1]) <= res["max_item"]
+
+
+def test_header_index_named_loading_and_selection(tmp_path):
+    """the orchestrator partitions on the header index and every rank reads only its own tensors"""
+    from safetensors.torch import save_file
+    a = {"w1": torch.randn(8, 256).to(torch.bfloat16), "b1": torch.randn(64).to(torch.bfloat16)}
+    b = {"w2": torch.randn(4, 1024).to(torch.float16), "ids": torch.arange(200), "lm_head.weight": torch.randn(2, 128),
+         "empty": torch.zeros(0, 4)}
+    save_file(a, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file(b, str(tmp_path / "model-00002-of-00002.safetensors"))
+    ld = load_model_from_path(str(tmp_path), logger_level="ERROR")
+    idx = ld.index()
+    assert sorted(idx) == ["b1", "empty", "ids", "lm_head.weight", "w1", "w2"]
+    assert idx["w1"].shape == (8, 256) and idx["w1"].dtype == torch.bfloat16 and idx["w1"].nbytes == 4096
+    assert idx["w2"].path.endswith("00002-of-00002.safetensors") and idx["ids"].dtype == torch.int64
+    quant, passed = cli.select_tensors(idx, skip_layers=["lm_head"])
+    assert quant == ["w2", "w1"]                                     # largest first (main.py:256)
+    assert sorted(passed) == ["b1", "empty", "ids", "lm_head.weight"]  # small / non-float / empty / skip_layers
+    got = ld.load_tensors(names=["w2", "b1"])
+    assert list(got) == ["b1", "w2"] and torch.equal(got["w2"], b["w2"]) and torch.equal(got["b1"], a["b1"])
+    with pytest.raises(KeyError):
+        ld.load_tensors(names=["nope"])
+    # two ranks: disjoint, complete, and each asks the loader for its own names only
+    costs = [(n, idx[n].nbytes) for n in quant + passed]
+    r0, r1 = (set(parallel.shard_for_rank(costs, 2, r)) for r in (0, 1))
+    assert not (r0 & r1) and (r0 | r1) == set(idx)
+
+
+@pytest.mark.timeout(300)
+def test_cli_two_ranks_fail_together_without_hanging(tmp_path):
+    """a rank that cannot do its work still reaches the metadata gather (here: both refuse the CPU); the job ends
+    with exit code 1 instead of waiting for the collective's timeout, and the process group is destroyed"""
+    from safetensors.torch import save_file
+    save_file({"w": torch.randn(4, 256)}, str(tmp_path / "m.safetensors"))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=os.path.join(ROOT, "awq-converter_b200"))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", "-m", "awq_quantizer.main",
+                        "--model_id", str(tmp_path), "--output_dir", str(tmp_path / "out"), "--log_level", "ERROR"],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode != 0
+    assert "no CPU execution path" in (r.stderr + r.stdout)
+    assert not os.path.exists(tmp_path / "out" / "metadata.json") or \
+        json.load(open(tmp_path / "out" / "metadata.json"))["num_tensors"] == 0

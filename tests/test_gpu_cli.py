@@ -89,3 +89,50 @@ def test_cli_calibration_file_runs_search(native_lib, cuda_device, tmp_path):
     assert int(r["best_idx"]) == int(want["best_idx"]) and torch.equal(r["qweight"], want["qweight"])
     assert torch.equal(r["awq_scale"], want["awq_scale"])
     assert "awq_scale" not in got["layers.0.fc2.weight"]
+
+
+def test_cli_passthrough_of_unquantized_tensors(native_lib, cuda_device, tmp_path):
+    """tensors the selection rules leave out (numel < 128, non-float) are not dropped as in the reference
+    (main.py:243-253): bf16 goes through K3 (bf16 -> fp16, tensor_utils.py:10-22), the rest is copied unchanged"""
+    from safetensors.torch import load_file
+    from awq_quantizer import main as cli
+    model, tensors = make_model(tmp_path)
+    out = str(tmp_path / "out_pt")
+    rc = cli.main(["--model_id", model, "--output_dir", out, "--device", "cuda:0", "--log_level", "ERROR"])
+    assert rc == 0
+    md = json.load(open(os.path.join(out, "metadata.json")))
+    assert md["passthrough"] == {"norm.weight": "passthrough.safetensors", "position_ids": "passthrough.safetensors"}
+    p = load_file(os.path.join(out, "passthrough.safetensors"))
+    assert p["norm.weight"].dtype == torch.float16
+    assert torch.equal(p["norm.weight"].view(torch.int16), O.bf16_to_fp16(tensors["norm.weight"]).view(torch.int16))
+    assert torch.equal(p["position_ids"], tensors["position_ids"])
+
+
+@pytest.mark.timeout(600)
+def test_cli_under_torchrun_two_ranks(native_lib, cuda_device, tmp_path):
+    """one process per rank, each loading and quantizing only its LPT share, one metadata gather (gloo here: the
+    test box may have a single GPU, which both ranks then share -- NCCL refuses duplicate devices)"""
+    import subprocess
+    import sys
+    model, tensors = make_model(tmp_path)
+    out = str(tmp_path / "out_tr")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AWQ_DIST_BACKEND="gloo", PYTHONPATH=os.path.join(root, "awq-converter_b200"))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543", "-m", "awq_quantizer.main",
+                        "--model_id", model, "--output_dir", out, "--pack", "--save_safetensors", "--log_level", "ERROR"],
+                       capture_output=True, text=True, env=env, timeout=500)
+    assert r.returncode == 0, r.stderr[-3000:]
+    md = json.load(open(os.path.join(out, "metadata.json")))
+    expect = ["layers.0.fc1.weight", "layers.0.fc1.bias", "layers.0.fc2.weight", "ragged.weight"]
+    assert sorted(md["tensor_to_chunk"]) == sorted(expect) and md["world_size"] == 2 and md["failed_ranks"] == []
+    assert sorted(md["passthrough"]) == ["norm.weight", "position_ids"]
+    assert any(f.startswith("rank0_") for f in md["files"]) and any(f.startswith("rank1_") for f in md["files"])
+    from safetensors.torch import load_file
+    flat = {}
+    for f in md["files"]:
+        flat.update(load_file(os.path.join(out, f)))
+    for n in expect:
+        want = O.pack_result(O.group_quant_vec(tensors[n], 4, 128, False, False))
+        assert torch.equal(flat[n + ".qweight"], want["qweight"]) and torch.equal(flat[n + ".qzeros"], want["qzeros"]), n
+        assert torch.equal(flat[n + ".scales"].view(torch.int16), want["scales"].view(torch.int16)), n

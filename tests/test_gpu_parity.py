@@ -421,22 +421,40 @@ def test_no_out_of_bounds_writes(native_lib, cuda_device):
         assert L.awqk_bf16_to_fp16(w.data_ptr(), h_v.data_ptr(), C * K, None) == 0
         torch.cuda.synchronize()
         assert _canaries_intact(out_b, C * K * 4) and _canaries_intact(h_b, C * K * 2)
-    # fake-quant delta (both kernels) and the GEMM's err vector
+    # fake-quant delta and the GEMM's err vector
     C, K, n = 37, 1280, 3
     w = datagen.weights((C, K), "bf16", 3).to(dev)
     s = (torch.rand((n, K), device=dev) + 0.5)
-    rws = torch.empty_like(s)
-    for ws in (None, rws.data_ptr()):
-        dw_b, dw_v = _guarded(n * C * K * 2, dev)
-        assert L.awqk_fakequant_delta(w.data_ptr(), N.BF16, C, K, 128, 4, 0, s.data_ptr(), n, dw_v.data_ptr(), ws, None) == 0
-        torch.cuda.synchronize()
-        assert _canaries_intact(dw_b, n * C * K * 2)
+    dw_b, dw_v = _guarded(n * C * K * 2, dev)
+    assert L.awqk_fakequant_delta(w.data_ptr(), N.BF16, C, K, 128, 4, 0, s.data_ptr(), n, dw_v.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert _canaries_intact(dw_b, n * C * K * 2)
     x = datagen.activations(70, K, "bf16", 5).to(dev)
     e_b, e_v = _guarded(n * 8, dev)
     e_v.zero_()
     assert L.awqk_sqerr_gemm(x.data_ptr(), dw_v.data_ptr(), 70, C, K, n, e_v.data_ptr(), None) == 0
     torch.cuda.synchronize()
     assert _canaries_intact(e_b, n * 8) and float(e_v.view(torch.float64).min()) > 0
+    # the one-call search: minimum workspace (ring of delta slabs + counters) and all outputs between canaries
+    import ctypes
+    for (C, K, T) in ((37, 1280, 70), (300, 1024, 260)):
+        w = datagen.weights((C, K), "bf16", 3).to(dev)
+        x = datagen.activations(T, K, "bf16", 5).to(dev)
+        mn = ctypes.c_size_t(0)
+        L.awqk_workspace_bytes(C, K, T, n, 0, ctypes.byref(mn))
+        G = K // 128
+        sizes = {"ws": mn.value, "err": n * 8, "best": 4, "s": K * 4, "qp": C * K // 8 * 4, "sc": C * G * 2, "z": C * G * 4,
+                 "zq": C * (-(-G // 8)) * 4}
+        bufs = {k: _guarded(v, dev) for k, v in sizes.items()}
+        v = {k: b[1] for k, b in bufs.items()}
+        assert v["ws"].data_ptr() % 256 == 0
+        rc = L.awqk_scale_search(w.data_ptr(), N.BF16, C, K, x.data_ptr(), T, None, n, 128, 4, 0, v["err"].data_ptr(),
+                                 v["best"].data_ptr(), v["s"].data_ptr(), None, v["qp"].data_ptr(), v["sc"].data_ptr(),
+                                 v["z"].data_ptr(), v["zq"].data_ptr(), v["ws"].data_ptr(), mn.value, None)
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        for k, (b, _) in bufs.items():
+            assert _canaries_intact(b, sizes[k]), (C, K, T, k)
 
 
 @pytest.mark.parametrize("shape", [(64, 256), (136, 1024), (8, 8 * 128), (200, 520)])

@@ -11,5 +11,5 @@ rws = torch.empty_like(sg)
 dw = torch.empty((n, C, K), dtype=torch.bfloat16, device=dev)
 st = torch.cuda.current_stream(dev).cuda_stream
 for _ in range(3):
-    N.check(L.awqk_fakequant_delta(w.data_ptr(), N.BF16, C, K, 128, 4, 0, sg.data_ptr(), n, dw.data_ptr(), rws.data_ptr(), st))
+    N.check(L.awqk_fakequant_delta(w.data_ptr(), N.BF16, C, K, 128, 4, 0, sg.data_ptr(), n, dw.data_ptr(), st))
 torch.cuda.synchronize(); print("ok")

@@ -13,7 +13,7 @@ err = torch.zeros(n, dtype=torch.float64, device=dev)
 big = torch.empty(256 << 20, dtype=torch.uint8, device=dev); big2 = torch.empty_like(big)
 A, B = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 def gemm(s): N.check(L.awqk_sqerr_gemm(x.data_ptr(), dw1.data_ptr(), T, C, K, n, err.data_ptr(), s.cuda_stream))
-def delta(s): N.check(L.awqk_fakequant_delta(w.data_ptr(), N.BF16, C, K, 128, 4, 0, sg.data_ptr(), n, dw2.data_ptr(), rws.data_ptr(), s.cuda_stream))
+def delta(s): N.check(L.awqk_fakequant_delta(w.data_ptr(), N.BF16, C, K, 128, 4, 0, sg.data_ptr(), n, dw2.data_ptr(), s.cuda_stream))
 def copy(s):
     with torch.cuda.stream(s): big2.copy_(big)
 def run(fa, fb, reps=10):

@@ -29,7 +29,7 @@ for s in shapes:
     rws = torch.empty_like(sg)
     dw = torch.empty((n_grid, C, K), dtype=torch.bfloat16, device=dev)
     err = torch.zeros(n_grid, dtype=torch.float64, device=dev)
-    d_ms, _ = timeit(lambda: [N.check(L.awqk_fakequant_delta(ws[s].data_ptr(), N.BF16, C, K, g, 4, 0, sg.data_ptr(), n_grid, dw.data_ptr(), rws.data_ptr(), st)) for _ in range(5)])
+    d_ms, _ = timeit(lambda: [N.check(L.awqk_fakequant_delta(ws[s].data_ptr(), N.BF16, C, K, g, 4, 0, sg.data_ptr(), n_grid, dw.data_ptr(), st)) for _ in range(5)])
     g_ms, _ = timeit(lambda: [N.check(L.awqk_sqerr_gemm(xs[K].data_ptr(), dw.data_ptr(), T, C, K, n_grid, err.data_ptr(), st)) for _ in range(5)])
     fl = 2.0 * T * C * K * n_grid
     res[s] = (d_ms / 5, g_ms / 5)
