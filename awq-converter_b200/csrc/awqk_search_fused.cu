@@ -2,16 +2,18 @@
 // kernel -- the fake-quant delta operand is produced by warps of the same CTAs that run the tcgen05 GEMM, while
 // the tensor pipe is busy, instead of by a separate kernel that writes [n_grid, C, K] bf16 to HBM first.
 //
-//   CTA pair (cluster of 2, one per SM pair, persistent):
-//     warps 0-7   PRODUCERS   dW units: 8 rows x 512 columns of one slab (256 W rows x K for one alpha), the
-//                             same arithmetic as the stand-alone kernel (delta16, awqk_search.cuh) -> ring slot
-//                             in global memory (L2 resident) -> ready[slab] += 1 (release)
-//     warps 8-11  EPILOGUE    tcgen05.ld of the accumulator, sum of squares, one fp64 atomic per warp and tile
-//     warp  12    TMA         waits ready[slab] == units (acquire + cross-proxy fence), then streams X and dW
-//                             k-blocks into the 6-stage SWIZZLE_128B ring (cp.async.bulk.tensor, cta_group::2)
-//     warp  13    MMA         leader CTA only: tcgen05.mma.cta_group::2 (M = 256 across the pair, N = 256),
-//                             TMEM double buffered; after the last k-block of a tile has LANDED it adds 1 to
-//                             done[slab] (release): the ring slot may be overwritten once all m-tiles are done
+//   CTA pair (cluster of 2, one per SM pair, persistent), 15 warps per CTA placed by scheduler (warp % 4):
+//     9 PRODUCER warps (0-2, 4-6, 8-10)  dW units: 8 rows x 512 columns of one slab (256 W rows x K for one
+//                             alpha), the same arithmetic as the stand-alone kernel (delta16, awqk_search.cuh)
+//                             -> ring slot in global memory (L2 resident) -> ready[slab] += 1 (release)
+//     warp 3   MMA            leader CTA only, ONE elected thread: tcgen05.mma.cta_group::2 (M = 256 across the
+//                             pair, N = 256), TMEM double buffered; after the last k-block of a tile has LANDED it
+//                             adds 1 to done[slab] (release): the slot may be overwritten once all m-tiles are done
+//     warp 7   TMA            waits ready[slab] == units (acquire + cross-proxy fence), then streams X and dW
+//                             k-blocks into the 7-stage SWIZZLE_128B ring (cp.async.bulk.tensor, cta_group::2)
+//     warps 11-14 EPILOGUE    tcgen05.ld of the accumulator, sum of squares, one fp64 atomic per warp and tile
+//   The MMA thread's instruction stream paces the tensor pipe (4 UMMAs per 512 tensor cycles).  It shares its
+//   scheduler with the TMA warp and one epilogue warp only -- never with a producer warp.
 //
 //   slab q = n_tile * n_grid + alpha (alpha fastest: the 256 W rows stay hot for the whole grid);
 //   tile  = q * m_tiles + m_tile -> the m_tiles pairs that consume a slab run side by side;
@@ -31,15 +33,17 @@
 namespace awqk {
 
 constexpr int kfBM = 128, kfBN = 256, kfBNh = 128, kfBK = 64;   // per-CTA A rows, pair N, per-CTA B rows
-constexpr int kfStages = 6;
+constexpr int kfStages = 7;
 constexpr int kfABytes = kfBM * kfBK * 2;
 constexpr int kfBBytes = kfBNh * kfBK * 2;
 constexpr int kfStageBytes = kfABytes + kfBBytes;
-constexpr int kfProducerWarps = 8;
-constexpr int kfThreads = (kfProducerWarps + 6) * 32;           // 448
+constexpr int kfProducerWarps = 9;
+constexpr int kfThreads = 15 * 32;                              // 480: see the role table in the kernel
 constexpr uint32_t kfTmemCols = 512;
 constexpr int kfSlabRows = 256;
 constexpr int kfUnitRows = 8, kfUnitCols = 512;
+constexpr int kfCtr = 32;                                      // one counter per 128-byte line (uint32 stride):
+                                                               // pollers of different slabs hit different L2 lines
 
 // ---- bounded waits (a protocol bug must fault, not hang the device) --------------------------------------------
 constexpr unsigned long long kfWaitLimitNs = 8000000000ull;    // 8 s
@@ -75,13 +79,16 @@ __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-__device__ __forceinline__ void wait_counter(const uint32_t* p, uint32_t target) {
+__device__ __forceinline__ void wait_counter(const uint32_t* p, uint32_t target, unsigned sleep_ns) {
   if (ld_acquire_gpu(p) >= target) return;
   const unsigned long long t0 = global_ns();
   while (ld_acquire_gpu(p) < target) {
-    __nanosleep(200);
+    __nanosleep(sleep_ns);
     if (global_ns() - t0 > kfWaitLimitNs) __trap();
   }
+}
+__device__ __forceinline__ void producer_bar() {               // named barrier 1: the producer warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(kfProducerWarps * 32) : "memory");
 }
 
 template <typename WT, int G, int BITS>
@@ -106,7 +113,13 @@ search_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int total_tiles = n_slabs * mp_tiles;
   const int col_blocks = (K + kfUnitCols - 1) / kfUnitCols;
   const int units_per_slab = (kfSlabRows / kfUnitRows) * col_blocks;
-  constexpr int kTmaWarp = kfProducerWarps + 4, kMmaWarp = kfProducerWarps + 5;
+  // warp roles by scheduler (a warp runs on sub-partition warp % 4): the MMA issuer and the TMA warp share
+  // sub-partition 3 with one epilogue warp only, so no producer warp ever competes with them for issue slots
+  //   warp  0 1 2 | 3   | 4 5 6 | 7   | 8 9 10 | 11  12 13 14
+  //   role  P P P | MMA | P P P | TMA | P P P  | epilogue (TMEM lane quarter = warp % 4)
+  constexpr int kMmaWarp = 3, kTmaWarp = 7;
+  const bool is_producer = (warp & 3) < 3 && warp < 11;
+  const int pw = (warp >> 2) * 3 + (warp & 3);                 // producer index 0..8
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kfStages; ++s) {
@@ -131,26 +144,35 @@ search_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp < kfProducerWarps) {
+  if (is_producer) {
     // ===================== delta producers =====================
     const bool sym = sym_i != 0;
     const float qmin = sym ? -(float)(1 << (BITS - 1)) : 0.0f;
     const float qmax = sym ? (float)((1 << (BITS - 1)) - 1) : (float)((1 << BITS) - 1);
     const int64_t n_units = (int64_t)n_slabs * units_per_slab;
     const int64_t stride = (int64_t)gridDim.x * kfProducerWarps;
-    int checked = -1;                                          // last slab whose ring slot was seen free
+    int checked = ring - 1;                                    // slabs <= checked may be written (their slot is free)
+    // every producer warp of the CTA runs the same number of rounds (a warp without a unit in the last round only
+    // joins the barrier): ONE lane per CTA polls the ring, not one per warp
 #pragma unroll 1
-    for (int64_t v = (int64_t)blockIdx.x * kfProducerWarps + warp; v < n_units; v += stride) {
+    for (int64_t v0 = (int64_t)blockIdx.x * kfProducerWarps; v0 < n_units; v0 += stride) {
+      const int64_t v = v0 + pw;
+      const int64_t v_hi = min(v0 + kfProducerWarps - 1, n_units - 1);
+      const int q_lo = (int)(v0 / units_per_slab), q_hi = (int)(v_hi / units_per_slab);   // <= 2 distinct slabs
+      if (q_hi > checked) {                                    // CTA uniform
+        if (pw == 0 && lane == 0) {                            // every m-tile of the slab that used the slot has landed
+          if (q_lo > checked) wait_counter(done + (int64_t)(q_lo - ring) * kfCtr, (uint32_t)mp_tiles, 500);
+          if (q_hi != q_lo) wait_counter(done + (int64_t)(q_hi - ring) * kfCtr, (uint32_t)mp_tiles, 500);
+        }
+        producer_bar();
+        checked = q_hi;
+      }
+      if (v >= n_units) continue;
       const int q = (int)(v / units_per_slab);
       const int u = (int)(v - (int64_t)q * units_per_slab);
       const int rb = u / col_blocks, cb = u - rb * col_blocks;
       const int nt = q / n_grid, a = q - nt * n_grid;
       const int slot = q % ring;
-      if (q >= ring && q != checked) {                         // every m-tile of the slab that used this slot has landed
-        if (lane == 0) wait_counter(done + (q - ring), (uint32_t)mp_tiles);
-        __syncwarp();
-        checked = q;
-      }
       const int col = cb * kfUnitCols + lane * 16;
       const bool cvalid = col < K;
       float2 sv[8], rs[8];
@@ -198,17 +220,17 @@ search_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       __threadfence();
       fence_proxy_async_global();
       __syncwarp();
-      if (lane == 0) red_release_gpu_add(ready + q, 1u);
+      if (lane == 0) red_release_gpu_add(ready + (int64_t)q * kfCtr, 1u);
     }
   } else if (warp == kTmaWarp) {
     // ===================== TMA (both CTAs; completion lands on the LEADER's full barrier) ==========
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, ph = 1;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const int q = tile / mp_tiles;
         const int mp = tile - q * mp_tiles;
         const int slot = q % ring;
-        wait_counter(ready + q, (uint32_t)units_per_slab);     // the whole slab has been produced
+        wait_counter(ready + (int64_t)q * kfCtr, (uint32_t)units_per_slab, 100);   // the whole slab has been produced
         fence_proxy_async_global();
         for (int kb = 0; kb < k_blocks; ++kb) {
           mb_wait_bounded(empty0 + 8 * stage, ph);             // own slot free (multicast commit from the leader)
@@ -222,9 +244,14 @@ search_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer: one thread of the leader CTA =====================
-    if (rank == 0) {
+    // ===================== MMA issuer: ONE elected thread of the leader CTA runs the whole loop ==========
+    // (this instruction stream paces the tensor pipe -- 4 UMMAs per 512 tensor cycles -- so it is kept short:
+    // descriptors advance by adds, nothing is recomputed per k-block, and the warp sits on a scheduler it
+    // shares with no producer warp, see the role table above)
+    if (rank == 0 && elect_one()) {
       uint32_t stage = 0, ph = 0;
+      const uint32_t lo0 = desc_lo_sw128(base);
+      uint32_t alo = lo0;
       int it = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
         const int q = tile / mp_tiles;
@@ -233,24 +260,22 @@ search_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mb_wait_bounded(tempty0 + 8 * ab, aph ^ 1u);           // both CTAs' epilogues drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + ab * kfBN;
+        uint32_t acc = 0u;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mb_wait_bounded(full0 + 8 * stage, ph);              // both CTAs' A and B halves have landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (lane == 0) {
-            const uint32_t sa = base + stage * kfStageBytes;
-            const uint64_t adesc = desc_sw128(sa);
-            const uint64_t bdesc = desc_sw128(sa + kfABytes);
-#pragma unroll
-            for (int k = 0; k < kfBK / 16; ++k) umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, (kb | k) ? 1u : 0u);
-            umma2_commit_mc(empty0 + 8 * stage);               // frees the slot in BOTH CTAs
-            if (kb == k_blocks - 1) {
-              umma2_commit_mc(tfull0 + 8 * ab);
-              red_release_gpu_add(done + q, 1u);               // the slab's last k-block is in shared memory
-            }
-          }
-          __syncwarp();
-          if (++stage == kfStages) { stage = 0; ph ^= 1u; }
+          const uint32_t blo = alo + (kfABytes >> 4);
+          umma2_bf16_lo(d_tmem, alo, blo, acc);
+          umma2_bf16_lo(d_tmem, alo + 2, blo + 2, 1u);
+          umma2_bf16_lo(d_tmem, alo + 4, blo + 4, 1u);
+          umma2_bf16_lo(d_tmem, alo + 6, blo + 6, 1u);
+          acc = 1u;
+          umma2_commit_mc(empty0 + 8 * stage);                 // frees the slot in BOTH CTAs
+          alo += (kfStageBytes >> 4);
+          if (++stage == kfStages) { stage = 0; ph ^= 1u; alo = lo0; }
         }
+        umma2_commit_mc(tfull0 + 8 * ab);
+        red_release_gpu_add(done + (int64_t)q * kfCtr, 1u);    // the slab's last k-block is in shared memory
       }
     }
   } else {
@@ -301,7 +326,7 @@ search_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 size_t fused_slab_bytes(int64_t K) { return (size_t)kfSlabRows * (size_t)K * 2; }
 
 size_t fused_sync_bytes(int64_t C, int n_grid) {
-  return (size_t)ceil_div(C, kfSlabRows) * (size_t)n_grid * 2 * sizeof(uint32_t);
+  return (size_t)ceil_div(C, kfSlabRows) * (size_t)n_grid * 2 * kfCtr * sizeof(uint32_t);
 }
 
 // slabs being consumed at any time ~ pairs / m_tiles; production wants a few more to run ahead
@@ -311,7 +336,7 @@ void fused_ring_depths(int64_t C, int64_t K, int64_t T, int n_grid, int* ring_mi
   const int64_t mp_tiles = ceil_div(T, 256);
   const int64_t in_flight = ceil_div(74, mp_tiles) + 1;       // 148 SMs -> 74 pairs
   *ring_min = (int)std::min<int64_t>(n_slabs, in_flight + 2);
-  *ring_pref = (int)std::min<int64_t>(n_slabs, in_flight + 14);
+  *ring_pref = (int)std::min<int64_t>(n_slabs, in_flight + 5);   // measured: a deeper ring only adds dead lines to L2
 }
 
 template <typename WT, int G, int BITS>
@@ -368,8 +393,8 @@ int launch_search_fused(const void* w, int dtype, int64_t C, int64_t K, const vo
     if (!encode_bf16_sw128(&map_ring, ring_base, 3, dims, strides, kfBNh)) return AWQK_E_BADARG;
   }
   uint32_t* ready = reinterpret_cast<uint32_t*>(sync);
-  uint32_t* done = ready + n_slabs;
-  AWQK_CUDA(cudaMemsetAsync(sync, 0, (size_t)n_slabs * 2 * sizeof(uint32_t), st));
+  uint32_t* done = ready + n_slabs * kfCtr;
+  AWQK_CUDA(cudaMemsetAsync(sync, 0, (size_t)n_slabs * 2 * kfCtr * sizeof(uint32_t), st));
   auto* ring_bf = reinterpret_cast<__nv_bfloat16*>(ring_base);
 #define AWQK_FUSED(WT, GG, BB)                                                                                      \
   return launch_fused_t<WT, GG, BB>(map_x, map_ring, reinterpret_cast<const WT*>(w), s_grid, ring_bf, C, (int)K,  \

@@ -21,7 +21,7 @@
 namespace awqk {
 
 constexpr int k2BM = 128, k2BN = 256, k2BNh = 128, k2BK = 64;   // per-CTA A rows, pair N, per-CTA B rows
-constexpr int k2Stages = 6;
+constexpr int k2Stages = 7;
 constexpr int k2ABytes = k2BM * k2BK * 2;    // 16 KiB
 constexpr int k2BBytes = k2BNh * k2BK * 2;   // 16 KiB
 constexpr int k2StageBytes = k2ABytes + k2BBytes;
@@ -70,7 +70,7 @@ sqerr_gemm2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs; completion lands on the LEADER's full barrier) ==========
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, ph = 1;
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         const int mp = tile % mp_tiles;
@@ -89,9 +89,13 @@ sqerr_gemm2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: one thread of the leader CTA =====================
-    if (rank == 0) {
+    // ===================== MMA issuer: ONE elected thread of the leader CTA runs the whole loop ==========
+    // (the loop must stay short: it is the pacing instruction stream of the tensor pipe -- 4 UMMAs per
+    // 512 tensor cycles; descriptors are advanced by adds, nothing is recomputed per k-block)
+    if (rank == 0 && elect_one()) {
       uint32_t stage = 0, ph = 0;
+      const uint32_t lo0 = desc_lo_sw128(base);
+      uint32_t alo = lo0;
       int it = 0;
       for (int tile = pair; tile < total_tiles; tile += n_pairs, ++it) {
         const uint32_t ab = (uint32_t)it & 1u;
@@ -99,21 +103,21 @@ sqerr_gemm2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mb_wait(tempty0 + 8 * ab, aph ^ 1u);                   // both CTAs' epilogues drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + ab * k2BN;
+        uint32_t acc = 0u;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mb_wait(full0 + 8 * stage, ph);                      // both CTAs' A and B halves have landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (lane == 0) {
-            const uint32_t sa = base + stage * k2StageBytes;
-            const uint64_t adesc = desc_sw128(sa);
-            const uint64_t bdesc = desc_sw128(sa + k2ABytes);
-#pragma unroll
-            for (int k = 0; k < k2BK / 16; ++k) umma2_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, (kb | k) ? 1u : 0u);
-            umma2_commit_mc(empty0 + 8 * stage);               // frees the slot in BOTH CTAs
-            if (kb == k_blocks - 1) umma2_commit_mc(tfull0 + 8 * ab);
-          }
-          __syncwarp();
-          if (++stage == k2Stages) { stage = 0; ph ^= 1u; }
+          const uint32_t blo = alo + (k2ABytes >> 4);
+          umma2_bf16_lo(d_tmem, alo, blo, acc);
+          umma2_bf16_lo(d_tmem, alo + 2, blo + 2, 1u);
+          umma2_bf16_lo(d_tmem, alo + 4, blo + 4, 1u);
+          umma2_bf16_lo(d_tmem, alo + 6, blo + 6, 1u);
+          acc = 1u;
+          umma2_commit_mc(empty0 + 8 * stage);                 // frees the slot in BOTH CTAs
+          alo += (k2StageBytes >> 4);
+          if (++stage == k2Stages) { stage = 0; ph ^= 1u; alo = lo0; }
         }
+        umma2_commit_mc(tfull0 + 8 * ab);
       }
     }
   } else {

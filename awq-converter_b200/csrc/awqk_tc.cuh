@@ -83,6 +83,26 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {   // arrive on `
       "h"((uint16_t)3)
       : "memory");
 }
+// one lane of the (converged) warp; the compiler knows that elect.sync yields a single active lane, which keeps
+// the tcgen05 operands in uniform registers without a per-instruction lane loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// low word of the SWIZZLE_128B K-major descriptor; additive in the byte offset (>> 4) inside shared memory
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void umma2_bf16_lo(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(alo), "r"(blo), "r"(kIdescPair256), "r"(accumulate), "r"(kDescHiSw128)
+      : "memory");
+}
 __device__ __forceinline__ void tm_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

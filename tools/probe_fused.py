@@ -14,7 +14,9 @@ ap.add_argument("--shapes", default="256x512,512x1024,1024x1024,4096x4096,14336x
 ap.add_argument("--tokens", type=int, default=2048)
 ap.add_argument("--n_grid", type=int, default=20)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--ring", default="pref", help="pref | min | <bytes>")
+ap.add_argument("--ring", default="pref", help="comma list of: pref | min | <number of slabs>")
+ap.add_argument("--sustain-ms", type=float, default=0.0, help="time each variant over at least this long (power-capped regime)")
+ap.add_argument("--no-staged", action="store_true")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 T, n = args.tokens, args.n_grid
@@ -39,24 +41,44 @@ for spec in args.shapes.split(","):
     st = N.stream_ptr(dev)
     _, grid, xb = S.activation_grid(x, n, st)
     pref, mn = S.workspace_bytes(C, K, T, n)
-    nbytes = pref if args.ring == "pref" else mn if args.ring == "min" else int(args.ring)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    slab = 256 * K * 2
+    n_slabs = -(-C // 256) * n
+    ring_min = min(n_slabs, -(-74 // -(-T // 256)) + 3)        # fused_ring_depths(): in flight + 2
+    header = mn - ring_min * slab                               # counters + scores in front of the ring
     out = {}
-
-    def fused():
-        out["r"] = S.scale_search(w, xb, grid, bits=4, group_size=128, symmetric=False, workspace=ws)
 
     def staged():
         out["s"] = S.search_device_staged(w, x, grid, bits=4, group_size=128, symmetric=False)
 
-    f_ms = timed(fused, args.reps)
-    s_ms = timed(staged, args.reps)
-    ef = (out["r"]["err_mean"] * float(T * C)).cpu()
-    es = out["s"].cpu()
-    rel = float(((ef - es).abs() / es).max())
     flops = 2.0 * T * C * K * n
-    print(json.dumps({"shape": [C, K], "tokens": T, "n_grid": n, "workspace_mb": round(nbytes / 2**20, 1),
-                      "fused_ms": round(f_ms, 3), "staged_ms": round(s_ms, 3),
-                      "fused_tflops": round(flops / f_ms / 1e9, 1), "staged_tflops": round(flops / s_ms / 1e9, 1),
-                      "max_rel_diff_scores": rel, "best_fused": int(out["r"]["best_idx"]),
-                      "best_staged": int(torch.argmin(es))}), flush=True)
+    s_ms = None
+    if not args.no_staged:
+        s_ms = timed(staged, args.reps)
+    for ring in args.ring.split(","):
+        if ring == "pref":
+            nbytes = pref
+        elif ring == "min":
+            nbytes = mn
+        else:                       # explicit slab count: header (everything before the ring) + slabs
+            nbytes = max(mn, header + int(ring) * slab)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+        def fused():
+            out["r"] = S.scale_search(w, xb, grid, bits=4, group_size=128, symmetric=False, workspace=ws)
+
+        f_ms = timed(fused, args.reps)
+        rec = {"shape": [C, K], "tokens": T, "n_grid": n, "ring": ring, "workspace_mb": round(nbytes / 2**20, 1),
+               "slab_mb": round(slab / 2**20, 2), "fused_ms": round(f_ms, 3), "fused_tflops": round(flops / f_ms / 1e9, 1)}
+        if args.sustain_ms:
+            reps = max(3, int(args.sustain_ms / f_ms))
+            f_sus = timed(fused, reps)
+            rec.update({"fused_sustained_ms": round(f_sus, 3), "fused_sustained_tflops": round(flops / f_sus / 1e9, 1),
+                        "sustained_reps": reps})
+        if s_ms is not None:
+            ef = (out["r"]["err_mean"] * float(T * C)).cpu()
+            es = out["s"].cpu()
+            rec.update({"staged_ms": round(s_ms, 3), "staged_tflops": round(flops / s_ms / 1e9, 1),
+                        "max_rel_diff_scores": float(((ef - es).abs() / es).max()),
+                        "best_fused": int(out["r"]["best_idx"]), "best_staged": int(torch.argmin(es))})
+        print(json.dumps(rec), flush=True)
+        del ws
