@@ -223,22 +223,25 @@ search_select_kernel(const double* __restrict__ err_sum, int n_grid, double deno
 // ------------------------------------------------------------------------------------------
 struct SearchPlan {
   size_t off_colsum, off_mnmx, off_grid, off_err, off_sync, off_ring, total_min, total_pref;
-  int ring_min, ring_pref;
+  FusedPlan fused;
+  int rc;
 };
 static inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static SearchPlan plan_search(int64_t C, int64_t K, int64_t T, int n_grid, bool own_grid) {
   SearchPlan p{};
+  p.rc = fused_plan(C, K, T, n_grid, &p.fused);
+  if (p.rc != AWQK_OK) return p;
   size_t o = 0;
   p.off_colsum = o; o += own_grid ? al256((size_t)K * 8) : 0;
   p.off_mnmx = o;   o += own_grid ? al256((size_t)n_grid * 2 * 4) : 0;
   p.off_grid = o;   o += own_grid ? al256((size_t)n_grid * K * 4) : 0;
   p.off_err = o;    o += al256((size_t)n_grid * 8);
-  p.off_sync = o;   o += al256(fused_sync_bytes(C, n_grid));
+  p.off_sync = o;   o += al256(p.fused.sync_bytes);
   p.off_ring = o;
-  fused_ring_depths(C, K, T, n_grid, &p.ring_min, &p.ring_pref);
-  p.total_min = o + (size_t)p.ring_min * fused_slab_bytes(K);
-  p.total_pref = o + (size_t)p.ring_pref * fused_slab_bytes(K);
+  const size_t per_depth = (size_t)p.fused.g.smax * p.fused.entry_bytes;
+  p.total_min = o + (size_t)p.fused.depth_min * per_depth;
+  p.total_pref = o + (size_t)p.fused.depth_pref * per_depth;
   return p;
 }
 
@@ -309,6 +312,10 @@ extern "C" size_t awqk_workspace_bytes(int64_t C, int64_t K, int64_t T, int n_gr
     return 0;
   }
   const SearchPlan p = plan_search(C, K, T, n_grid, have_s_grid == 0);
+  if (p.rc != AWQK_OK) {
+    if (minimum) *minimum = 0;
+    return 0;
+  }
   if (minimum) *minimum = p.total_min;
   return p.total_pref;
 }
@@ -329,10 +336,11 @@ extern "C" int awqk_scale_search(const void* w, int dtype, int64_t C, int64_t K,
        reinterpret_cast<uintptr_t>(best_s)) & 15u)
     return AWQK_E_ALIGN;
   if (reinterpret_cast<uintptr_t>(workspace) & 255u) return AWQK_E_ALIGN;
-  const SearchPlan p = plan_search(C, K, T, n_grid, s_grid_in == nullptr);
-  if (workspace_bytes < p.total_min) return AWQK_E_WORKSPACE;
   DeviceGuard guard(w);
   if (guard.status != AWQK_OK) return guard.status;
+  const SearchPlan p = plan_search(C, K, T, n_grid, s_grid_in == nullptr);      // (for the device of w)
+  if (p.rc != AWQK_OK) return p.rc;
+  if (workspace_bytes < p.total_min) return AWQK_E_WORKSPACE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   const bool sym = symmetric != 0;
@@ -350,9 +358,10 @@ extern "C" int awqk_scale_search(const void* w, int dtype, int64_t C, int64_t K,
   }
   double* err_sum = reinterpret_cast<double*>(ws + p.off_err);
   AWQK_CUDA(cudaMemsetAsync(err_sum, 0, (size_t)n_grid * 8, st));
-  const int ring = (int)std::min<size_t>((size_t)p.ring_pref, (workspace_bytes - p.off_ring) / fused_slab_bytes(K));
+  const size_t per_depth = (size_t)p.fused.g.smax * p.fused.entry_bytes;
+  const int depth = (int)std::min<size_t>((size_t)p.fused.depth_pref, (workspace_bytes - p.off_ring) / per_depth);
   int rc = launch_search_fused(w, dtype, C, K, x_bf16, T, s_grid, n_grid, group_size, bits, sym, err_sum,
-                               ws + p.off_sync, ws + p.off_ring, ring, st);
+                               ws + p.off_sync, ws + p.off_ring, depth, st);
   if (rc != AWQK_OK) return rc;
   search_select_kernel<<<(unsigned)std::min<int64_t>(ceil_div(K, 256), 64), 256, 0, st>>>(
       err_sum, n_grid, (double)T * (double)C, s_grid, K, err_mean, best_idx, best_s);

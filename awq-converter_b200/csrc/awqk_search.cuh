@@ -152,13 +152,24 @@ int launch_fakequant_delta(const void* w, int dtype, int64_t C, int64_t K, int g
                            int n_s, __nv_bfloat16* dw, cudaStream_t st);
 
 // awqk_search_fused.cu: producer warps + tcgen05 GEMM in one persistent kernel.  The delta operand lives in a
-// ring of `ring` slabs (256 W rows x K, bf16) that stays (mostly) L2 resident; `sync` holds the per-slab
+// ring of panel entries (256 W rows x Kc columns, bf16) that stays L2 resident; `sync` holds the per-entry
 // ready / done counters (zeroed by the launcher).
-size_t fused_slab_bytes(int64_t K);
-size_t fused_sync_bytes(int64_t C, int n_grid);
-void fused_ring_depths(int64_t C, int64_t K, int64_t T, int n_grid, int* ring_min, int* ring_pref);
+struct FusedGeom {                // geometry of one launch (host-computed, identical in planning and launch)
+  int K, Kc, panels;              // columns, panel width (2048, or K itself when K <= 2048), ceil(K / Kc)
+  int n_grid, mp_tiles, n_tiles;
+  int smax, depth, ring;          // slab positions per wave, FIFO depth in panels, ring = smax * depth entries
+  int sym;
+};
+struct FusedPlan {
+  FusedGeom g;
+  int pairs;                      // CTA pairs of the launch
+  int64_t n_entries;              // ring entries over the whole launch (counter arrays)
+  size_t sync_bytes, entry_bytes; // counters; one ring entry
+  int depth_min, depth_pref;      // ring bytes = g.smax * depth * entry_bytes
+};
+int fused_plan(int64_t C, int64_t K, int64_t T, int n_grid, FusedPlan* plan);    // queries the current device
 int launch_search_fused(const void* w, int dtype, int64_t C, int64_t K, const void* x_bf16, int64_t T,
                         const float* s_grid, int n_grid, int g, int bits, bool sym, double* err_sum, void* sync,
-                        void* ring_base, int ring, cudaStream_t st);
+                        void* ring_base, int depth, cudaStream_t st);
 
 }  // namespace awqk

@@ -14,7 +14,7 @@ ap.add_argument("--shapes", default="256x512,512x1024,1024x1024,4096x4096,14336x
 ap.add_argument("--tokens", type=int, default=2048)
 ap.add_argument("--n_grid", type=int, default=20)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--ring", default="pref", help="comma list of: pref | min | <number of slabs>")
+ap.add_argument("--ring", default="pref", help="comma list of: pref | min | <bytes>")
 ap.add_argument("--sustain-ms", type=float, default=0.0, help="time each variant over at least this long (power-capped regime)")
 ap.add_argument("--no-staged", action="store_true")
 args = ap.parse_args()
@@ -41,10 +41,6 @@ for spec in args.shapes.split(","):
     st = N.stream_ptr(dev)
     _, grid, xb = S.activation_grid(x, n, st)
     pref, mn = S.workspace_bytes(C, K, T, n)
-    slab = 256 * K * 2
-    n_slabs = -(-C // 256) * n
-    ring_min = min(n_slabs, -(-74 // -(-T // 256)) + 3)        # fused_ring_depths(): in flight + 2
-    header = mn - ring_min * slab                               # counters + scores in front of the ring
     out = {}
 
     def staged():
@@ -59,8 +55,8 @@ for spec in args.shapes.split(","):
             nbytes = pref
         elif ring == "min":
             nbytes = mn
-        else:                       # explicit slab count: header (everything before the ring) + slabs
-            nbytes = max(mn, header + int(ring) * slab)
+        else:                       # bytes
+            nbytes = max(mn, int(ring))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
         def fused():
@@ -68,7 +64,7 @@ for spec in args.shapes.split(","):
 
         f_ms = timed(fused, args.reps)
         rec = {"shape": [C, K], "tokens": T, "n_grid": n, "ring": ring, "workspace_mb": round(nbytes / 2**20, 1),
-               "slab_mb": round(slab / 2**20, 2), "fused_ms": round(f_ms, 3), "fused_tflops": round(flops / f_ms / 1e9, 1)}
+               "fused_ms": round(f_ms, 3), "fused_tflops": round(flops / f_ms / 1e9, 1)}
         if args.sustain_ms:
             reps = max(3, int(args.sustain_ms / f_ms))
             f_sus = timed(fused, reps)
