@@ -38,6 +38,7 @@ SIGNATURES = {
     "awqk_workspace_bytes": (C.c_size_t, [_i64, _i64, _i64, _int, _int, C.POINTER(C.c_size_t)]),
     "awqk_sqerr_gemm": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _vp, _vp]),
     "awqk_export_autoawq": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp, _vp, _vp]),
+    "awqk_host_prefault": (_int, [_vp, C.c_size_t, _int]),
     "awqk_pipe_create": (_int, [_int, C.c_size_t, C.POINTER(_vp)]),
     "awqk_pipe_destroy": (None, [_vp]),
     "awqk_pipe_quant_host": (_int, [_vp, _vp, _int, _i64, _i64, _int, _int, _int, _int, _vp, _vp, _vp,

@@ -275,6 +275,28 @@ class AWQQuantizer:
             dev = self._cuda_device()
             self._check_zero_point_mode()
             want = {n: t for n, t in tensors.items() if n in activations}
+            rest = {n: t for n, t in tensors.items() if n not in want}
+            # the tensors without activations (embeddings, norms ...) go through the gather pipeline on a helper
+            # thread WHILE the searched ones stream through the tensor-core path: their K1 launches are HBM bound
+            # and slip in between the search kernels, their host copies use otherwise idle cores
+            other: Dict[str, dict] = {}
+            side_err: list = []
+
+            def run_rest():
+                try:
+                    torch.cuda.set_device(dev)
+                    other.update(self.quantize_model(rest, pack=pack, chunk_bytes=chunk_bytes, pipeline=pipeline,
+                                                     keep_unpacked=keep_unpacked, _pin=pin))
+                except BaseException as e:                       # reported below, on the caller's thread
+                    side_err.append(e)
+
+            side = None
+            if rest:
+                # a persistent worker: the gather pipeline's pinned rings belong to the thread that uses them
+                if getattr(self, "_side_pool", None) is None:
+                    from concurrent.futures import ThreadPoolExecutor
+                    self._side_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="awq-rest")
+                side = self._side_pool.submit(run_rest)
             searched = {}
             try:
                 searched = quantize_model_with_search(self, want, activations, dev, pack=pack, keep_unpacked=keep_unpacked,
@@ -283,6 +305,9 @@ class AWQQuantizer:
                 # the streamed model-level search failed as a whole (e.g. one bad shape, out of memory): search tensor
                 # by tensor instead, so that one offender cannot silently turn AWQ scaling off for all the others
                 self.logger.error(f"Streamed activation-aware search failed ({e}); searching tensor by tensor")
+                if side is not None:
+                    side.result()
+                    side = None
                 torch.cuda.synchronize(dev)
                 keep = (not pack) if keep_unpacked is None else bool(keep_unpacked or not pack)
                 for name, t in want.items():
@@ -294,9 +319,14 @@ class AWQQuantizer:
                     except Exception as e2:
                         self.logger.error(f"Activation-aware search failed for {name}: {e2}; quantizing it without "
                                           f"AWQ scaling (no 'awq_scale' in its result)")
-            rest = {n: t for n, t in tensors.items() if n not in searched}
-            other = self.quantize_model(rest, pack=pack, chunk_bytes=chunk_bytes, pipeline=pipeline,
-                                        keep_unpacked=keep_unpacked, _pin=pin) if rest else {}
+            if side is not None:
+                side.result()
+            if side_err:
+                self.logger.error(f"Quantization of the tensors without activations failed: {side_err[0]}")
+            missed = {n: t for n, t in want.items() if n not in searched}
+            if missed:
+                other.update(self.quantize_model(missed, pack=pack, chunk_bytes=chunk_bytes, pipeline=pipeline,
+                                                 keep_unpacked=keep_unpacked, _pin=pin))
             return {n: (searched[n] if n in searched else other[n]) for n in tensors if n in searched or n in other}
         if not pack:
             from .arena import HostArena, pipe_eligible, quantize_arena

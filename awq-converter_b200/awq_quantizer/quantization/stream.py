@@ -5,8 +5,9 @@
     caller's thread   wave i  : SearchPipeline (delta + tcgen05 GEMM streams) -> argmin -> K1 on W * s_best
     output stream     wave i-1: results -> pinned ring slot -> drain thread -> ordinary host tensors
 
-Two device slots and two pinned staging slots for the weights, three pinned ring slots for the results, CUDA
-events between the streams, one host synchronisation at the end.  No pinned allocation proportional to the model
+Three device slots and three pinned staging slots for the weights, three pinned ring slots for the results (drained
+into ONE pre-faulted, huge-page host arena per call), CUDA events between the streams, one host synchronisation at
+the end.  No pinned allocation proportional to the model
 (cudaHostAlloc runs at ~2.3 GB/s, 20x slower than this pipeline).  Replaces the reference's per-tensor
 ``tensor.to(device)`` ... ``.cpu()`` round trips (awq.py:402, 410-412; main.py:353-392) for the searched tensors.
 """
@@ -14,6 +15,7 @@ from __future__ import annotations
 
 import queue
 import threading
+import time
 from typing import Dict, List, Optional
 
 import torch
@@ -56,7 +58,7 @@ class WaveUploader(threading.Thread):
         self.dev, self.tensors, self.waves = dev, tensors, waves
         host_waves = [[n for n in w if tensors[n].device.type != "cuda"] for w in waves]
         slot_bytes = max([sum(_align(_nbytes(tensors[n])) for n in w) for w in host_waves] + [256])
-        self.n_slots = min(2, len(waves))
+        self.n_slots = min(3, len(waves))                      # 3: the staging copy never waits for a slot (measured 0.14 s of 0.63)
         self.d_slot = [torch.empty(slot_bytes, dtype=torch.uint8, device=dev) for _ in range(self.n_slots)]
         need_stage = any(not tensors[n].is_pinned() for w in host_waves for n in w)
         self.h_slot = [torch.empty(slot_bytes, dtype=torch.uint8, pin_memory=True)
@@ -64,6 +66,7 @@ class WaveUploader(threading.Thread):
         self.stream = torch.cuda.Stream(dev)
         self.stream.wait_stream(torch.cuda.current_stream(dev))
         self.ready: "queue.Queue" = queue.Queue()
+        self.stats = {"stage_copy_s": 0.0, "wait_slot_s": 0.0, "staged_bytes": 0}
         self._released = [None] * len(waves)                   # CUDA events, set by release()
         self._released_flag = [threading.Event() for _ in waves]
         self._abort = threading.Event()
@@ -82,11 +85,13 @@ class WaveUploader(threading.Thread):
             for wi, wave in enumerate(self.waves):
                 slot = wi % self.n_slots
                 if wi >= self.n_slots:
+                    t0 = time.perf_counter()
                     h2d_done[wi - self.n_slots].synchronize()              # pinned staging slot is free again
                     while not self._released_flag[wi - self.n_slots].wait(0.05):
                         if self._abort.is_set():
                             return
                     self.stream.wait_event(self._released[wi - self.n_slots])   # device slot is free again
+                    self.stats["wait_slot_s"] += time.perf_counter() - t0
                 views, off = {}, 0
                 for n in wave:
                     t = self.tensors[n]
@@ -98,7 +103,10 @@ class WaveUploader(threading.Thread):
                     src = t.detach()
                     if not src.is_pinned():
                         hv = self.h_slot[slot][off:off + nb].view(t.dtype).view(t.shape)
+                        t0 = time.perf_counter()
                         N.host_copy(hv, src)
+                        self.stats["stage_copy_s"] += time.perf_counter() - t0
+                        self.stats["staged_bytes"] += nb
                         src = hv
                     with torch.cuda.stream(self.stream):
                         dv.copy_(src, non_blocking=True)
@@ -118,8 +126,20 @@ class ResultSink:
     ``pin_results=False``: ring of three pinned slots + a drain thread that copies each finished slot into ordinary
     tensors.  ``pin_results=True``: one pinned arena per (wave, dtype), written by the D2H copies directly."""
 
-    def __init__(self, dev: torch.device, slot_bytes: int, n_waves: int, pin_results: bool):
+    def __init__(self, dev: torch.device, slot_bytes: int, n_waves: int, pin_results: bool, total_bytes: int = 0):
         self.dev, self.pin = dev, pin_results
+        # pageable mode: ONE host arena for all results of the call (the per-tensor results are views of it), with
+        # transparent huge pages requested and every page touched by a few threads in the background -- a drain
+        # copy into fresh small allocations runs at page-fault speed (~10 GB/s), into touched memory at memcpy speed
+        self._arena = None
+        self._arena_off = 0
+        self._prefault = None
+        if not pin_results and total_bytes > 0:
+            self._arena = torch.empty(total_bytes, dtype=torch.uint8)
+            self._prefault = threading.Thread(
+                target=lambda: N.lib().awqk_host_prefault(self._arena.data_ptr(), total_bytes, 0),
+                name="awq-prefault", daemon=True)
+            self._prefault.start()
         self.stream = torch.cuda.Stream(dev)
         self.host: Dict[str, Dict[str, torch.Tensor]] = {}
         self._inflight = []                                       # pinned mode: (device tensors, D2H-done event)
@@ -129,6 +149,7 @@ class ResultSink:
         self._free = threading.Semaphore(max(1, len(self._ring)))
         self._err: list = []
         self._thread = None
+        self.stats = {"drain_copy_s": 0.0, "drain_wait_event_s": 0.0, "submit_wait_free_s": 0.0, "drained_bytes": 0}
         if not pin_results:
             self._thread = threading.Thread(target=self._drain, name="awq-drain", daemon=True)
             self._thread.start()
@@ -141,11 +162,20 @@ class ResultSink:
                 if item is None:
                     return
                 slot, entries, ev, keep = item
+                t0 = time.perf_counter()
                 ev.synchronize()
+                t1 = time.perf_counter()
                 for name, k, off, nb, dt, shape in entries:
-                    final = torch.empty(shape, dtype=dt)
+                    if self._arena is not None and self._arena_off + nb <= self._arena.numel():
+                        final = self._arena[self._arena_off:self._arena_off + nb].view(dt).view(shape)
+                        self._arena_off += _align(nb)
+                    else:
+                        final = torch.empty(shape, dtype=dt)
                     N.host_copy(final, self._ring[slot][off:off + nb].view(dt).view(shape))
                     self.host.setdefault(name, {})[k] = final
+                    self.stats["drained_bytes"] += nb
+                self.stats["drain_wait_event_s"] += t1 - t0
+                self.stats["drain_copy_s"] += time.perf_counter() - t1
                 del keep, item
                 self._free.release()
         except BaseException as e:
@@ -156,7 +186,9 @@ class ResultSink:
         """``computed``: recorded after the kernels that produced ``dev_out``; ``keep``: anything that must stay
         alive until the copies have finished"""
         if not self.pin:
+            t0 = time.perf_counter()
             self._free.acquire()                                  # the slot's previous wave has been drained
+            self.stats["submit_wait_free_s"] += time.perf_counter() - t0
             if self._err:
                 raise self._err[0]
             slot = wi % len(self._ring)
@@ -198,6 +230,8 @@ class ResultSink:
         self._q.put(None)
         if self._thread is not None:
             self._thread.join(timeout=60 if failed else None)
+        if self._prefault is not None:
+            self._prefault.join(timeout=60)
         if failed:
             return
         if self._err:
@@ -239,13 +273,19 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
                                     keep_unpacked=keep_unpacked) for n in w) for w in waves)
     cur = torch.cuda.current_stream(dev)
     uploader = WaveUploader(dev, tensors, waves)
-    sink = ResultSink(dev, slot_out, len(waves), pin_results)
+    total_out = sum(result_bytes(tensors[n], group_size=qz.group_size, bits=qz.bits, n_grid=qz.n_grid, pack=pack,
+                                 keep_unpacked=keep_unpacked) for n in names)
+    sink = ResultSink(dev, slot_out, len(waves), pin_results, total_bytes=total_out)
     uploader.start()
     x_dev: Dict[int, torch.Tensor] = {}
     pipe = SearchPipeline(dev, bits=qz.bits, group_size=qz.group_size, symmetric=qz.symmetric, n_grid=qz.n_grid)
+    t_begin = time.perf_counter()
+    wait_upload = 0.0
     try:
         for wi, wave in enumerate(waves):
+            t0 = time.perf_counter()
             item = uploader.ready.get()
+            wait_upload += time.perf_counter() - t0
             if isinstance(item, BaseException):
                 raise item
             views, uploaded = item
@@ -267,7 +307,12 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
             computed.record(cur)
             uploader.release(wi, computed)
             sink.submit(wi, dev_out, views, computed)
+        t_submitted = time.perf_counter()
         sink.close()
+        # where the host-side time of this call went (read by tools / the bench; seconds)
+        qz.last_stream_stats = {"waves": len(waves), "submit_loop_s": t_submitted - t_begin,
+                                "final_drain_s": time.perf_counter() - t_submitted, "wait_for_upload_s": wait_upload,
+                                **uploader.stats, **sink.stats}
     except BaseException:
         uploader.abort()
         sink.close(failed=True)

@@ -368,6 +368,28 @@ extern "C" int awqk_host_copy(void* dst, const void* src, size_t bytes, int thre
   return AWQK_OK;
 }
 
+extern "C" int awqk_host_prefault(void* ptr, size_t bytes, int threads) {
+  if (ptr == nullptr && bytes != 0) return AWQK_E_BADARG;
+  if (bytes == 0) return AWQK_OK;
+  advise_huge(ptr, bytes);
+  const int n = std::max(1, threads > 0 ? std::min(threads, 16) : pipe_threads());
+  const size_t per = ((bytes + n - 1) / n + 4095) & ~(size_t)4095;
+  auto touch = [](uint8_t* b, size_t len) {     // write-fault every page without changing its content (atomic | 0)
+    for (size_t o = 0; o < len; o += 4096) __atomic_fetch_or(b + o, (uint8_t)0, __ATOMIC_RELAXED);
+    if (len) __atomic_fetch_or(b + len - 1, (uint8_t)0, __ATOMIC_RELAXED);
+  };
+  std::vector<std::thread> ts;
+  uint8_t* base = static_cast<uint8_t*>(ptr);
+  for (int t = 1; t < n; ++t) {
+    const size_t off = (size_t)t * per;
+    if (off >= bytes) break;
+    ts.emplace_back(touch, base + off, std::min(per, bytes - off));
+  }
+  touch(base, std::min(per, bytes));
+  for (auto& t : ts) t.join();
+  return AWQK_OK;
+}
+
 extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* const* src, const int64_t* numel,
                                       int64_t row_len, int dtype, int group_size, int bits, int symmetric, int arith,
                                       int32_t* q_unpacked_host, uint32_t* q_packed_host, void* scales_f16_host,

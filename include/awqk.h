@@ -209,6 +209,10 @@ AWQK_API int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* con
  * core moves ~10 GB/s, a PCIe 5 x16 link wants 50: the staging copies between pageable tensors and the pinned
  * rings of the Python-side streams (quantization/search.py) go through this. */
 AWQK_API int awqk_host_copy(void* dst, const void* src, size_t bytes, int threads);
+/* first-touch a fresh pageable host buffer from `threads` threads (0 = default), after asking for transparent huge
+ * pages on it: result arrays that the drain copies would otherwise fault in page by page (~10 GB/s instead of
+ * memcpy speed).  Content is not changed (atomic OR with 0), so it may overlap with writes into the buffer. */
+AWQK_API int awqk_host_prefault(void* ptr, size_t bytes, int threads);
 /* wait for everything queued on the pipe */
 AWQK_API int awqk_pipe_sync(awqk_pipe* p);
 
