@@ -59,7 +59,7 @@ def workspace_bytes(C: int, K: int, T: int, n_grid: int):
 
 def scale_search(w: torch.Tensor, xb: torch.Tensor, s_grid: torch.Tensor, *, bits: int, group_size: int,
                  symmetric: bool, workspace: torch.Tensor, outputs: Optional[Dict[str, torch.Tensor]] = None,
-                 st: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                 st: Optional[int] = None, select: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """ONE native call (awqk_scale_search): scores for every row of ``s_grid``, device-side argmin, winning scale
     vector and -- when ``outputs`` holds 'scales' (+ any of 'tensor_q', 'qweight', 'zero_points', 'qzeros') -- the
     final column-scaled K1 pass.  Nothing synchronises with the host."""
@@ -67,9 +67,12 @@ def scale_search(w: torch.Tensor, xb: torch.Tensor, s_grid: torch.Tensor, *, bit
     C, K = w.shape
     T = xb.shape[0]
     n_grid = s_grid.shape[0]
-    err = torch.empty(n_grid, dtype=torch.float64, device=dev)
-    best = torch.empty((), dtype=torch.int32, device=dev)
-    s_best = torch.empty(K, dtype=torch.float32, device=dev)
+    if select is not None:                       # caller-owned buffers ('err_mean' fp64 [n_grid], 'best_idx', 's_best')
+        err, best, s_best = select["err_mean"], select["best_idx"], select["s_best"]
+    else:
+        err = torch.empty(n_grid, dtype=torch.float64, device=dev)
+        best = torch.empty((), dtype=torch.int32, device=dev)
+        s_best = torch.empty(K, dtype=torch.float32, device=dev)
     o = outputs or {}
     N.check(N.lib().awqk_scale_search(
         N.ptr(w), N.dtype_code(w.dtype), C, K, N.ptr(xb), T, N.ptr(s_grid), n_grid, group_size, bits, int(symmetric),
@@ -188,7 +191,8 @@ class SearchPipeline:
         return self.grid_cache[key]
 
     def submit(self, name: str, w: torch.Tensor, x: torch.Tensor,
-               outputs: Optional[Dict[str, torch.Tensor]] = None) -> None:
+               outputs: Optional[Dict[str, torch.Tensor]] = None,
+               select: Optional[Dict[str, torch.Tensor]] = None) -> None:
         _check(w, x, self.g)
         C, K = w.shape
         T = x.shape[0]
@@ -198,7 +202,7 @@ class SearchPipeline:
             self.workspace = torch.empty(pref, dtype=torch.uint8, device=self.dev)
         s_grid, xb, _ = self._grid(x)
         r = scale_search(w, xb, s_grid, bits=self.bits, group_size=self.g, symmetric=self.sym,
-                         workspace=self.workspace, outputs=outputs)
+                         workspace=self.workspace, outputs=outputs, select=select)
         self.pending.append((name, r))
 
     def finish(self, keep_grids: bool = False):

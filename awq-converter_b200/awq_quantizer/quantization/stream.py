@@ -59,10 +59,12 @@ class WaveUploader(threading.Thread):
         host_waves = [[n for n in w if tensors[n].device.type != "cuda"] for w in waves]
         slot_bytes = max([sum(_align(_nbytes(tensors[n])) for n in w) for w in host_waves] + [256])
         self.n_slots = min(3, len(waves))                      # 3: the staging copy never waits for a slot (measured 0.14 s of 0.63)
-        self.d_slot = [torch.empty(slot_bytes, dtype=torch.uint8, device=dev) for _ in range(self.n_slots)]
-        need_stage = any(not tensors[n].is_pinned() for w in host_waves for n in w)
-        self.h_slot = [torch.empty(slot_bytes, dtype=torch.uint8, pin_memory=True)
-                       for _ in range(self.n_slots)] if need_stage else []
+        # slots are allocated by the uploader thread itself, one by one, when first used: the first wave is on its
+        # way after ONE pinned allocation (cudaHostAlloc runs at ~2.5 GB/s), not after all three
+        self.slot_bytes = slot_bytes
+        self.need_stage = any(not tensors[n].is_pinned() for w in host_waves for n in w)
+        self.d_slot: List[Optional[torch.Tensor]] = [None] * self.n_slots
+        self.h_slot: List[Optional[torch.Tensor]] = [None] * self.n_slots
         self.stream = torch.cuda.Stream(dev)
         self.stream.wait_stream(torch.cuda.current_stream(dev))
         self.ready: "queue.Queue" = queue.Queue()
@@ -92,6 +94,10 @@ class WaveUploader(threading.Thread):
                             return
                     self.stream.wait_event(self._released[wi - self.n_slots])   # device slot is free again
                     self.stats["wait_slot_s"] += time.perf_counter() - t0
+                if self.d_slot[slot] is None:
+                    self.d_slot[slot] = torch.empty(self.slot_bytes, dtype=torch.uint8, device=self.dev)
+                    if self.need_stage:
+                        self.h_slot[slot] = torch.empty(self.slot_bytes, dtype=torch.uint8, pin_memory=True)
                 views, off = {}, 0
                 for n in wave:
                     t = self.tensors[n]
@@ -181,6 +187,24 @@ class ResultSink:
         except BaseException as e:
             self._err.append(e)
             self._free.release()
+
+    def submit_arena(self, wi: int, d_arena: torch.Tensor, used: int, entries, keep, computed: torch.cuda.Event):
+        """pageable mode: the wave's results sit in ONE device arena laid out like a ring slot -> one D2H copy.
+        ``entries``: [(name, key, offset, nbytes, dtype, shape)].  Returns the event of the copy (the device arena
+        may be rewritten after it)."""
+        t0 = time.perf_counter()
+        self._free.acquire()                                      # the slot's previous wave has been drained
+        self.stats["submit_wait_free_s"] += time.perf_counter() - t0
+        if self._err:
+            raise self._err[0]
+        slot = wi % len(self._ring)
+        self.stream.wait_event(computed)
+        with torch.cuda.stream(self.stream):
+            self._ring[slot][:used].copy_(d_arena[:used], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(self.stream)
+        self._q.put((slot, entries, done, keep))
+        return done
 
     def submit(self, wi: int, dev_out: Dict[str, Dict[str, torch.Tensor]], keep, computed: torch.cuda.Event) -> None:
         """``computed``: recorded after the kernels that produced ``dev_out``; ``keep``: anything that must stay
@@ -279,6 +303,13 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
     uploader.start()
     x_dev: Dict[int, torch.Tensor] = {}
     pipe = SearchPipeline(dev, bits=qz.bits, group_size=qz.group_size, symmetric=qz.symmetric, n_grid=qz.n_grid)
+    # pageable results: three rotating device arenas, each laid out like a result-ring slot (one D2H copy per wave)
+    use_arena = not pin_results
+    n_out = min(3, len(waves))
+    d_out: List[Optional[torch.Tensor]] = [None] * n_out
+    d_out_free: List[Optional[torch.cuda.Event]] = [None] * n_out
+    G_of = lambda K: K // qz.group_size
+    per = 32 // qz.bits
     t_begin = time.perf_counter()
     wait_upload = 0.0
     try:
@@ -290,23 +321,59 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
                 raise item
             views, uploaded = item
             cur.wait_event(uploaded)
-            wave_out = {}
+            wave_out, wave_sel, entries, off = {}, {}, [], 0
+            if use_arena:
+                oi = wi % n_out
+                if d_out[oi] is None:
+                    d_out[oi] = torch.empty(max(slot_out, 256), dtype=torch.uint8, device=dev)
+                if d_out_free[oi] is not None:
+                    cur.wait_event(d_out_free[oi])               # the arena's previous wave has left the device
+                arena = d_out[oi]
+
+                def carve(name, key, shape, dt):
+                    nonlocal off
+                    nb = 1
+                    for d in shape:
+                        nb *= d
+                    nb *= torch.empty((), dtype=dt).element_size()
+                    v = arena[off:off + nb].view(dt).view(shape)
+                    entries.append((name, key, off, nb, dt, tuple(shape)))
+                    off += _align(nb)
+                    return v
             for n in wave:
                 x = activations[n]
                 if id(x) not in x_dev:
                     x_dev[id(x)] = x.to(dev, non_blocking=True).contiguous()
                 C, K = views[n].shape
-                wave_out[n] = alloc_outputs(qz, C, K, dev, pack=pack, unpacked=keep_unpacked)
-                pipe.submit(n, views[n], x_dev[id(x)], outputs=wave_out[n])      # scores + argmin + final K1 pass
-            dev_out = {}
-            for name, mean, best, s_best in pipe.finish(keep_grids=True):
-                o = dict(wave_out[name])
-                o.update({"search_err": mean, "best_idx": best, "awq_scale": s_best})
-                dev_out[name] = o
+                if use_arena:
+                    G = G_of(K)
+                    o = {"scales": carve(n, "scales", (C, G), torch.float16),
+                         "zero_points": carve(n, "zero_points", (C, G), torch.int32)}
+                    if keep_unpacked:
+                        o["tensor_q"] = carve(n, "tensor_q", (C, K), torch.int32)
+                    if pack:
+                        o["qweight"] = carve(n, "qweight", (C, -(-K // per)), torch.int32)
+                        o["qzeros"] = carve(n, "qzeros", (C, -(-G // per)), torch.int32)
+                    wave_sel[n] = {"err_mean": carve(n, "search_err", (qz.n_grid,), torch.float64),
+                                   "best_idx": carve(n, "best_idx", (), torch.int32),
+                                   "s_best": carve(n, "awq_scale", (K,), torch.float32)}
+                    wave_out[n] = o
+                else:
+                    wave_out[n] = alloc_outputs(qz, C, K, dev, pack=pack, unpacked=keep_unpacked)
+                pipe.submit(n, views[n], x_dev[id(x)], outputs=wave_out[n], select=wave_sel.get(n))   # scores + argmin + final K1
+            results = pipe.finish(keep_grids=True)
             computed = torch.cuda.Event()
             computed.record(cur)
             uploader.release(wi, computed)
-            sink.submit(wi, dev_out, views, computed)
+            if use_arena:
+                d_out_free[wi % n_out] = sink.submit_arena(wi, arena, off, entries, views, computed)
+            else:
+                dev_out = {}
+                for name, mean, best, s_best in results:
+                    o = dict(wave_out[name])
+                    o.update({"search_err": mean, "best_idx": best, "awq_scale": s_best})
+                    dev_out[name] = o
+                sink.submit(wi, dev_out, views, computed)
         t_submitted = time.perf_counter()
         sink.close()
         # where the host-side time of this call went (read by tools / the bench; seconds)

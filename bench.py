@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--search-tokens", type=int, default=2048)
     ap.add_argument("--n-grid", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--profile", action="store_true",
+                    help="for ncu launch lists: one warm-up step, --steps timed steps, no other leg (not a bench number)")
     return ap.parse_args()
 
 
@@ -391,7 +393,7 @@ def run_native(args):
         return allmax(mine_ms), mine_ms
 
     # ---- device-resident leg: K whole conversions back to back ------------------------------------------------
-    warm = max(3, args.warmup)
+    warm = 1 if args.profile else max(3, args.warmup)
     for _ in range(warm):
         model.convert()
     clocks = ClockSampler(local)                   # sampled over the timed region of the headline number only
@@ -400,6 +402,13 @@ def run_native(args):
     clocks_step = clocks.stop()
     value = total_bytes / (ms_step * 1e-3) / 1e9
     timed_region_s = ms_step * args.steps * 1e-3
+
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "gpu_launches": model.launches * args.steps}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     # ---- dominant kernel: the fused score kernel, same launches as in the step, alone, back to back (sustained) ----
     roofline = None
