@@ -242,7 +242,7 @@ __device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
 }
 
 template <typename InT, int A, int G, bool SYM, bool UNPACKED, bool CS, int BITS>
-__global__ void __launch_bounds__(kV2Threads, (UNPACKED || CS || sizeof(InT) == 4) ? 2 : 3)
+__global__ void __launch_bounds__(kV2Threads, (UNPACKED || sizeof(InT) == 4) ? 2 : 3)
 group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out, V2ColScale csp) {
   static_assert(!CS || A == AR_F32, "column scaling is defined in fp32 arithmetic");
   static_assert(BITS == 4 || BITS == 8, "int4 or int8 codes");
@@ -262,7 +262,11 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
   constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + (int)CMAX);
 
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (UNPACKED ? kV2UnpStageBytes : 0));
+  // CS: the slab's 1024 fp32 column scales, one 128-byte row per lane (all 8 consumer warps walk the same columns),
+  // chunk (2c + h) of a lane stored at position (2c + h) ^ (lane & 7): conflict-free LDS.128 for every quarter warp
+  constexpr uint32_t CS_BYTES = CS ? kV2WarpTile * 4 : 0;
+  const uint32_t cs_sm = smem_u32(smem) + STAGES * STAGE_BYTES + (UNPACKED ? kV2UnpStageBytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (UNPACKED ? kV2UnpStageBytes : 0) + CS_BYTES);
   uint32_t full0 = smem_u32(bars);
   uint32_t empty0 = smem_u32(bars + STAGES);
   asm volatile("" : "+r"(full0), "+r"(empty0));   // keep the shared-window addresses in registers
@@ -276,6 +280,21 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
       mbar_init(empty0 + 8 * s, kV2ConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (CS && warp == 0) {                         // lane l: its 32 scales, in the rotated chunk order of the W loads
+    const int rot0 = (lane >> 1) & 3;
+    const float* sp0 = csp.s + (int64_t)(blockIdx.x % (unsigned)csp.n_slabs) * kV2WarpTile + lane * 32;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(sp0 + 8 * ((c + rot0) & 3) + 4 * h));
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cs_sm + (uint32_t)lane * 128u +
+                                                                     (uint32_t)(((2 * c + h) ^ (lane & 7)) << 4)),
+                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+      }
+    }
   }
   __syncthreads();
 
@@ -381,19 +400,10 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     qu_base = reinterpret_cast<uint8_t*>(out.q_unpacked + warp_e_first + 4 * lane);
   }
   const uint32_t qu_step = (uint32_t)e_stride * 4u;              // bytes per iteration (host keeps it < 2^32)
-  // CS: this thread's 32 column scales, in the rotated chunk order of the LDS below
-  float2 sreg[CS ? 16 : 1];
-  if (CS) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const float4* sp = reinterpret_cast<const float4*>(csp.s + slab_col + lane * 32 + 8 * ((c + rot) & 3));
-      const float4 a = __ldg(sp), b = __ldg(sp + 1);
-      sreg[4 * c] = make_float2(a.x, a.y);
-      sreg[4 * c + 1] = make_float2(a.z, a.w);
-      sreg[4 * c + 2] = make_float2(b.x, b.y);
-      sreg[4 * c + 3] = make_float2(b.z, b.w);
-    }
-  }
+  // CS: this lane's row of the column-scale table (read chunk by chunk inside the loop: 8 more LDS.128 per tile
+  // instead of 32 registers for the whole kernel -> 3 CTAs per SM like the flat mode)
+  const uint32_t cs_thr = cs_sm + (uint32_t)lane * 128u;
+  const uint32_t cs_x = (uint32_t)(lane & 7);
 
   PairQuant<A, QMIN, BITS> pq;
   pq.prepare();
@@ -422,10 +432,21 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     float2 xv[(CS || F32IN) ? 16 : 1];
     if (CS || F32IN) {
       // CS: x = fp32(w) * s[k]; fp32 input: x = w.  The group statistics are taken on x (3-input FMNMX)
+      if (CS) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        xv[i] = F32IN ? make_float2(__uint_as_float(wds[(2 * i) % (4 * NLD)]), __uint_as_float(wds[(2 * i + 1) % (4 * NLD)]))
-                      : __fmul2_rn(Packed<InT>::to_f2(wds[i % (4 * NLD)]), sreg[CS ? i : 0]);
+        for (int ch = 0; ch < 8; ++ch) {           // chunk ch = 2c + h: scales of words 4c + 2h, 4c + 2h + 1
+          float4 sv;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w)
+                       : "r"(cs_thr + (((uint32_t)ch ^ cs_x) << 4)));
+          xv[2 * ch] = __fmul2_rn(Packed<InT>::to_f2(wds[(2 * ch) % (4 * NLD)]), make_float2(sv.x, sv.y));
+          xv[2 * ch + 1] = __fmul2_rn(Packed<InT>::to_f2(wds[(2 * ch + 1) % (4 * NLD)]), make_float2(sv.z, sv.w));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          xv[i] = make_float2(__uint_as_float(wds[(2 * i) % (4 * NLD)]), __uint_as_float(wds[(2 * i + 1) % (4 * NLD)]));
+      }
       mn = fmin3_nan(xv[0].x, xv[0].y, xv[1].x);
       mx = fmax3_nan(xv[0].x, xv[0].y, xv[1].x);
       mn = v2_fmin_nan(mn, xv[1].y);
@@ -605,7 +626,7 @@ static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, V2ColScal
   int dev = 0, sms = 0;
   AWQK_CUDA(cudaGetDevice(&dev));
   AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t want = (int64_t)sms * ((UNPACKED || CS || sizeof(InT) == 4) ? 2 : 3);   // resident CTAs per SM (smem / register bound)
+  const int64_t want = (int64_t)sms * ((UNPACKED || sizeof(InT) == 4) ? 2 : 3);   // resident CTAs per SM (smem / register bound)
   int64_t n_tiles;
   unsigned grid;
   if (CS) {
@@ -623,7 +644,8 @@ static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, V2ColScal
   }
   constexpr bool F32IN = sizeof(InT) == 4;                         // (same constants as in the kernel)
   constexpr int STAGES = F32IN ? (UNPACKED ? 2 : 3) : kV2Stages;
-  const size_t smem = (size_t)STAGES * kV2CtaTile * sizeof(InT) + (UNPACKED ? kV2UnpStageBytes : 0) + 2 * STAGES * sizeof(uint64_t);
+  const size_t smem = (size_t)STAGES * kV2CtaTile * sizeof(InT) + (UNPACKED ? kV2UnpStageBytes : 0) +
+                      (CS ? kV2WarpTile * 4 : 0) + 2 * STAGES * sizeof(uint64_t);
   // the dynamic-smem opt-in is per (kernel instantiation, device): set once, then immutable
   static std::atomic<uint64_t> configured[2] = {{0}, {0}};
   const uint64_t bit = 1ull << (dev & 63);

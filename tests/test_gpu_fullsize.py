@@ -81,7 +81,11 @@ def test_k1_over_1e9_elements_vs_c_oracle(native_lib, cuda_device):
 
 
 @pytest.mark.parametrize("dt,g,sym,C,K,T", [("bf16", 128, False, 520, 1024, 300), ("fp16", 64, True, 256, 2048, 257),
-                                             ("fp32", 32, False, 300, 512, 128), ("bf16", 128, True, 1024, 4096, 1000)])
+                                             ("fp32", 32, False, 300, 512, 128), ("bf16", 128, True, 1024, 4096, 1000),
+                                             # ragged last panel (K = 2048 + 192), fewer rows than one slab
+                                             ("bf16", 64, False, 40, 2240, 200),
+                                             # more m-tiles than CTA pairs (a slab spans several waves), 3 panels
+                                             ("bf16", 128, False, 300, 4224, 19500)])
 def test_scale_search_one_call_c_abi(native_lib, cuda_device, dt, g, sym, C, K, T):
     """awqk_scale_search called directly (own grid from X inside the workspace, minimum workspace): scores ==
     stand-alone delta + GEMM stages, best = first minimum, best_s = that grid row, outputs == awqk_group_quant"""
