@@ -291,8 +291,23 @@ def _rank_work(args, logger, rank: int, world: int, local: int) -> dict:
             meta["error"] = f"Failed to load model: {e}"
             return meta
         quant_names, pass_names = select_tensors(index, args.skip_layers, logger)
-        if world > 1:                                    # rank-local shard (torchrun): by bytes, largest first
-            costs = [(n, index[n].nbytes) for n in quant_names] + [(n, index[n].nbytes) for n in pass_names]
+        calib_tokens = {}
+        if args.calibration_file and args.scale_method == "mse":
+            try:                                         # header only: which weights will be searched, and over how many tokens
+                from safetensors import safe_open
+                with safe_open(args.calibration_file, framework="pt") as f:
+                    calib_tokens = {k: f.get_slice(k).get_shape()[0] for k in f.keys()}
+            except Exception as e:
+                meta["error"] = f"Failed to read calibration file: {e}"
+                return meta
+        if world > 1:                                    # rank-local shard (torchrun), largest first: cost = bytes
+            # (main.py:410), or C*K*T for the linears that run the activation-aware search (tensor-core bound)
+            def cost(n):
+                info = index[n]
+                if n in calib_tokens and len(info.shape) == 2:
+                    return info.numel * max(2, int(calib_tokens[n]))
+                return info.nbytes
+            costs = [(n, cost(n)) for n in quant_names] + [(n, index[n].nbytes) for n in pass_names]
             mine = set(parallel.shard_for_rank(costs, world, rank))
             quant_names = [n for n in quant_names if n in mine]
             pass_names = [n for n in pass_names if n in mine]

@@ -205,6 +205,10 @@ class SearchPipeline:
                          workspace=self.workspace, outputs=outputs, select=select)
         self.pending.append((name, r))
 
+    def drop_grid(self, x: torch.Tensor) -> None:
+        """forget the cached grid of one activation tensor (its last linear has been submitted)"""
+        self.grid_cache.pop((x.data_ptr(), tuple(x.shape)), None)
+
     def finish(self, keep_grids: bool = False):
         """[(name, err_mean fp64 [n_grid] (device), best_idx (device int32 0-d), s_best (device fp32 [K]))] in
         submission order, without a host sync"""

@@ -302,6 +302,12 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
     sink = ResultSink(dev, slot_out, len(waves), pin_results, total_bytes=total_out)
     uploader.start()
     x_dev: Dict[int, torch.Tensor] = {}
+    # an activation tensor stays on the device from its first to its last wave only (q/k/v and gate/up share
+    # theirs); a whole model's calibration set is never resident at once
+    last_use: Dict[int, int] = {}
+    for wi_, wave_ in enumerate(waves):
+        for n_ in wave_:
+            last_use[id(activations[n_])] = wi_
     pipe = SearchPipeline(dev, bits=qz.bits, group_size=qz.group_size, symmetric=qz.symmetric, n_grid=qz.n_grid)
     # pageable results: three rotating device arenas, each laid out like a result-ring slot (one D2H copy per wave)
     use_arena = not pin_results
@@ -364,6 +370,8 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
             results = pipe.finish(keep_grids=True)
             computed = torch.cuda.Event()
             computed.record(cur)
+            for key in [k for k, last in last_use.items() if last == wi and k in x_dev]:
+                pipe.drop_grid(x_dev.pop(key))                   # same stream: the allocator may reuse it right away
             uploader.release(wi, computed)
             if use_arena:
                 d_out_free[wi % n_out] = sink.submit_arena(wi, arena, off, entries, views, computed)

@@ -85,6 +85,9 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void wait_counter(const uint32_t* p, uint32_t target, unsigned sleep_ns) {
   if (ld_acquire_gpu(p) >= target) return;
@@ -268,15 +271,21 @@ search_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const int q = tile / mp_tiles;
         const int mp = tile - q * mp_tiles;
         const int sp = q - wave_q_lo(wv);
+        auto units_of = [&](int j) {
+          return (uint32_t)((kfSlabRows / kfUnitRows) * ((panel_cols(j) + kfUnitCols - 1) / kfUnitCols));
+        };
+        // the counter of the NEXT panel is read while this panel's loads are issued (the load is in flight behind
+        // the TMA issue loop; an acquire round trip through a busy L2 otherwise opens a bubble at every panel start)
+        uint32_t seen = ld_acquire_gpu(ready + (int64_t)entry_of(wv, 0, sp) * kfCtr);
         for (int j = 0; j < panels; ++j) {
           const int e = entry_of(wv, j, sp);
           const int pcols = panel_cols(j);
-          const uint32_t units = (uint32_t)((kfSlabRows / kfUnitRows) * ((pcols + kfUnitCols - 1) / kfUnitCols));
-          wait_counter(ready + (int64_t)e * kfCtr, units, 100); // the whole panel has been produced
+          if (seen < units_of(j)) wait_counter(ready + (int64_t)e * kfCtr, units_of(j), 100);   // the whole panel has been produced
           fence_proxy_async_global();
           const int slot = e % g.ring;
           const int kbs = pcols / kfBK;
           for (int kb = 0; kb < kbs; ++kb) {
+            if (kb == 0 && j + 1 < panels) seen = ld_acquire_gpu(ready + (int64_t)entry_of(wv, j + 1, sp) * kfCtr);
             mb_wait_bounded(empty0 + 8 * stage, ph);           // own slot free (multicast commit from the leader)
             const uint32_t lbar = (full0 + 8 * stage) & kPeerMask;
             if (rank == 0) mb_expect_tx(full0 + 8 * stage, 2 * kfStageBytes);
@@ -322,8 +331,10 @@ search_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             alo += (kfStageBytes >> 4);
             if (++stage == kfStages) { stage = 0; ph ^= 1u; alo = lo0; }
           }
-          // the panel's last k-block is in shared memory: this tile no longer needs the ring entry
-          red_release_gpu_add(done + (int64_t)entry_of(it, j, sp) * kfCtr, 1u);
+          // the panel's last k-block is in shared memory (observed through its mbarrier): this tile no longer
+          // needs the ring entry.  Relaxed: the TMA reads have completed, this thread has nothing of its own to
+          // publish, and a release fence here would stall the thread that paces the tensor pipe once per panel
+          red_relaxed_gpu_add(done + (int64_t)entry_of(it, j, sp) * kfCtr, 1u);
         }
         umma2_commit_mc(tfull0 + 8 * ab);
       }
@@ -416,7 +427,9 @@ int fused_plan(int64_t C, int64_t K, int64_t T, int n_grid, FusedPlan* p) {
   p->sync_bytes = (size_t)n_entries * 2 * kfCtr * sizeof(uint32_t);
   p->entry_bytes = (size_t)kfSlabRows * Kc * 2;
   p->depth_min = (int)std::min<int64_t>(2, n_waves * panels);
-  p->depth_pref = (int)std::min<int64_t>(3, n_waves * panels);
+  // measured (tools/probe_fused.py --ring): the depth does not limit K <= 4096; for larger K every extra panel is
+  // L2 footprint (4096x14336: depth 2 -> 1163, depth 6 -> 1125 TFLOP/s)
+  p->depth_pref = (int)std::min<int64_t>(panels > 2 ? 2 : 3, n_waves * panels);
   p->g = FusedGeom{(int)K, Kc, panels, n_grid, (int)mp_tiles, (int)n_tiles, smax, 0, 0, 0};
   return AWQK_OK;
 }
