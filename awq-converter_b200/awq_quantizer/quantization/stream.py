@@ -53,16 +53,29 @@ class WaveUploader(threading.Thread):
     ``release(wi, event)`` with an event recorded after its last read of wave ``wi``: only then is the wave's
     device slot overwritten."""
 
-    def __init__(self, dev: torch.device, tensors: Dict[str, torch.Tensor], waves: List[List[str]]):
+    def __init__(self, dev: torch.device, tensors: Dict[str, torch.Tensor], waves: List[List[str]],
+                 activations: Optional[Dict[str, torch.Tensor]] = None, x_plan: Optional[dict] = None):
         super().__init__(name="awq-upload", daemon=True)
         self.dev, self.tensors, self.waves = dev, tensors, waves
         host_waves = [[n for n in w if tensors[n].device.type != "cuda"] for w in waves]
-        slot_bytes = max([sum(_align(_nbytes(tensors[n])) for n in w) for w in host_waves] + [256])
+        # calibration activations travel with the wave that needs them first, on the copy stream (not on the compute
+        # stream, and never as a blocking pageable copy on the consumer's thread)
+        self.x_plan = x_plan or {}                             # id(x) -> (device buffer, last wave of its previous occupant)
+        self.wave_acts: List[List[torch.Tensor]] = [[] for _ in waves]
+        seen = set()
+        for wi, w in enumerate(waves):
+            for n in w:
+                x = (activations or {}).get(n)
+                if x is not None and id(x) not in seen:
+                    seen.add(id(x))
+                    self.wave_acts[wi].append(x)
+        stage_acts = [sum(_align(_nbytes(x)) for x in xs if x.device.type != "cuda" and not x.is_pinned()) for xs in self.wave_acts]
+        slot_bytes = max([sum(_align(_nbytes(tensors[n])) for n in w) + a for w, a in zip(host_waves, stage_acts)] + [256])
         self.n_slots = min(3, len(waves))                      # 3: the staging copy never waits for a slot (measured 0.14 s of 0.63)
         # slots are allocated by the uploader thread itself, one by one, when first used: the first wave is on its
         # way after ONE pinned allocation (cudaHostAlloc runs at ~2.5 GB/s), not after all three
         self.slot_bytes = slot_bytes
-        self.need_stage = any(not tensors[n].is_pinned() for w in host_waves for n in w)
+        self.need_stage = any(not tensors[n].is_pinned() for w in host_waves for n in w) or any(stage_acts)
         self.d_slot: List[Optional[torch.Tensor]] = [None] * self.n_slots
         self.h_slot: List[Optional[torch.Tensor]] = [None] * self.n_slots
         self.stream = torch.cuda.Stream(dev)
@@ -118,6 +131,28 @@ class WaveUploader(threading.Thread):
                         dv.copy_(src, non_blocking=True)
                     views[n] = dv
                     off += _align(nb)
+                acts = {}
+                for x in self.wave_acts[wi]:                   # id(x) -> its device buffer (planned by the consumer)
+                    src = x.detach().contiguous()
+                    xd, prev_last = self.x_plan[id(x)]
+                    if prev_last >= 0:                         # the buffer's previous occupant has been read for the last time
+                        while not self._released_flag[prev_last].wait(0.05):
+                            if self._abort.is_set():
+                                return
+                        self.stream.wait_event(self._released[prev_last])
+                    if src.device.type != "cuda" and not src.is_pinned():
+                        nb = _nbytes(src)
+                        hv = self.h_slot[slot][off:off + nb].view(src.dtype).view(src.shape)
+                        t0 = time.perf_counter()
+                        N.host_copy(hv, src)
+                        self.stats["stage_copy_s"] += time.perf_counter() - t0
+                        self.stats["staged_bytes"] += nb
+                        src = hv
+                        off += _align(nb)
+                    with torch.cuda.stream(self.stream):
+                        xd.copy_(src, non_blocking=True)
+                    acts[id(x)] = xd
+                views["__activations__"] = acts
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
                 h2d_done.append(ev)
@@ -265,6 +300,36 @@ class ResultSink:
         self._inflight.clear()
 
 
+def plan_activation_buffers(waves: List[List[str]], activations: Dict[str, torch.Tensor], dev: torch.device,
+                            lookahead: int = 3) -> dict:
+    """Device buffers for the calibration activations: an activation tensor is resident from ``lookahead`` waves
+    before its first wave (the uploader runs that far ahead) to its last wave; tensors of one (shape, dtype) class
+    share a small set of buffers (interval colouring), so a whole model's calibration set is never resident at once.
+    Returns id(x) -> (device buffer, last wave of the buffer's previous occupant or -1).  Allocated by the caller's
+    thread: allocations on the uploader's thread / stream would go through cudaMalloc mid-pipeline."""
+    first: Dict[int, int] = {}
+    last: Dict[int, int] = {}
+    obj: Dict[int, torch.Tensor] = {}
+    for wi, wave in enumerate(waves):
+        for n in wave:
+            x = activations[n]
+            first.setdefault(id(x), wi)
+            last[id(x)] = wi
+            obj[id(x)] = x
+    plan, pools = {}, {}
+    for k in sorted(first, key=lambda k: first[k]):
+        x = obj[k]
+        cls = (tuple(x.shape), x.dtype)
+        pool = pools.setdefault(cls, [])                          # [buffer, last wave of its current occupant]
+        slot = next((p for p in pool if p[1] < first[k] - lookahead), None)
+        if slot is None:
+            slot = [torch.empty(x.shape, dtype=x.dtype, device=dev), -1]
+            pool.append(slot)
+        plan[k] = (slot[0], slot[1])
+        slot[1] = last[k]
+    return plan
+
+
 def result_bytes(t: torch.Tensor, *, group_size: int, bits: int, n_grid: int, pack: bool, keep_unpacked: bool) -> int:
     """bytes of one searched tensor's results in a ring slot"""
     C, K = t.shape
@@ -296,7 +361,8 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
     slot_out = max(sum(result_bytes(tensors[n], group_size=qz.group_size, bits=qz.bits, n_grid=qz.n_grid, pack=pack,
                                     keep_unpacked=keep_unpacked) for n in w) for w in waves)
     cur = torch.cuda.current_stream(dev)
-    uploader = WaveUploader(dev, tensors, waves)
+    x_plan = plan_activation_buffers(waves, activations, dev, lookahead=3)
+    uploader = WaveUploader(dev, tensors, waves, activations, x_plan)
     total_out = sum(result_bytes(tensors[n], group_size=qz.group_size, bits=qz.bits, n_grid=qz.n_grid, pack=pack,
                                  keep_unpacked=keep_unpacked) for n in names)
     sink = ResultSink(dev, slot_out, len(waves), pin_results, total_bytes=total_out)
@@ -327,6 +393,7 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
                 raise item
             views, uploaded = item
             cur.wait_event(uploaded)
+            x_dev.update(views.pop("__activations__"))
             wave_out, wave_sel, entries, off = {}, {}, [], 0
             if use_arena:
                 oi = wi % n_out
@@ -348,8 +415,6 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
                     return v
             for n in wave:
                 x = activations[n]
-                if id(x) not in x_dev:
-                    x_dev[id(x)] = x.to(dev, non_blocking=True).contiguous()
                 C, K = views[n].shape
                 if use_arena:
                     G = G_of(K)

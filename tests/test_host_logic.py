@@ -160,3 +160,27 @@ def test_stream_wave_planning():
     both = stream.result_bytes(t["a"], pack=True, keep_unpacked=True, **kw)
     assert packed - base == 64 * 32 * 4 + 256 and both - packed == 64 * 256 * 4      # qweight + one padded qzeros slot; int32 codes
     assert base >= 64 * 2 * 2 + 64 * 2 * 4 + 20 * 8 + 4 + 256 * 4 and base % 256 == 0
+
+
+def test_activation_buffer_plan():
+    """calibration activations share a few device buffers per shape class: occupants of one buffer never overlap
+    (with the uploader's lookahead), and every tensor knows which wave released its buffer"""
+    from awq_quantizer.quantization.stream import plan_activation_buffers
+    xs = [torch.zeros(4, 8) for _ in range(6)] + [torch.zeros(4, 16)]
+    acts = {f"t{i}": xs[i // 2] for i in range(12)}
+    acts["wide"] = xs[6]
+    waves = [[f"t{i}"] for i in range(12)] + [["wide"]]
+    plan = plan_activation_buffers(waves, acts, torch.device("cpu"), lookahead=2)
+    assert set(plan) == {id(x) for x in xs}
+    first = {id(xs[i]): 2 * i for i in range(6)}
+    last = {id(xs[i]): 2 * i + 1 for i in range(6)}
+    by_buf = {}
+    for k, (buf, prev_last) in plan.items():
+        assert tuple(buf.shape) == tuple([x for x in xs if id(x) == k][0].shape)
+        by_buf.setdefault(id(buf), []).append((k, prev_last))
+    assert len(by_buf) == 2 + 1                                  # 2 rotating 4x8 buffers at lookahead 2, one 4x16
+    for occupants in by_buf.values():
+        occupants = [o for o in occupants if o[0] in first]
+        occupants.sort(key=lambda o: first[o[0]])
+        for (ka, _), (kb, prev) in zip(occupants, occupants[1:]):
+            assert prev == last[ka] and last[ka] < first[kb] - 2
