@@ -68,7 +68,7 @@ def lib() -> C.CDLL:
                     except ValueError:
                         ranks = 1
                     if ranks > 1:
-                        os.environ["AWQK_PIPE_THREADS"] = str(max(2, min(8, (os.cpu_count() or 8) // ranks)))
+                        os.environ["AWQK_PIPE_THREADS"] = str(max(2, min(12, (os.cpu_count() or 8) // ranks)))
                 if not os.path.exists(LIB_PATH):
                     raise NativeError(
                         f"{LIB_PATH} not found: build it with `python awq-converter_b200/build.py` "

@@ -245,7 +245,9 @@ int pipe_threads() {
     int v = e ? atoi(e) : 0;
     if (v <= 0) {
       const unsigned hc = std::thread::hardware_concurrency();
-      v = hc >= 16 ? 8 : (hc >= 8 ? 4 : 2);     // measured on a 16-core host: 4 -> 0.84 s, 8 -> 0.59 s, 16 -> 0.86 s
+      // measured on a 16-core host, Llama-3-8B end to end (tools/probe_cold.py): 4 -> 0.71 s, 8 -> 0.60 s,
+      // 12 -> 0.57 s, 16 -> 0.57 s (the copies compete with the DMA engines for host DRAM, not for cores)
+      v = hc >= 16 ? 12 : (hc >= 8 ? 4 : 2);
     }
     return std::min(v, 16);
   }();
