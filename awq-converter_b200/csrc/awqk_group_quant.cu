@@ -458,15 +458,6 @@ int launch_group_quant_tma_cs(const void* w, int dtype, int64_t C, int64_t K, in
                               uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                               cudaStream_t st);
 
-static bool tma_path_enabled() {
-  // AWQK_FORCE_V1=1 keeps the register-path kernel for A/B measurements (read once, read-only)
-  static const bool enabled = []() {
-    const char* e = getenv("AWQK_FORCE_V1");
-    return !(e != nullptr && e[0] == '1');
-  }();
-  return enabled;
-}
-
 }  // namespace awqk
 
 using namespace awqk;
@@ -503,7 +494,7 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
 
   if (path == 1) {
     const bool tma_plain = (dtype == AWQK_BF16 || dtype == AWQK_FP16 || (dtype == AWQK_FP32 && bits == 4)) &&
-                           (q_packed != nullptr || q_unpacked != nullptr) && col_scale == nullptr && tma_path_enabled() &&
+                           (q_packed != nullptr || q_unpacked != nullptr) && col_scale == nullptr &&
                            (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0;
     // rows of 1 / 2 / 4 groups (fewer than a packed word): K1 v2 writes one zero-padded word per row itself
     const int full_log2 = (bits == 4) ? 3 : 2;                 // log2(zero points per word)
@@ -521,7 +512,7 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
       rc = launch_group_quant_tma(w, dtype, n, group_size, bits, sym, arith, q_packed, q_unpacked, scales_f16, zp,
                                   out.zp_packed, zq_log2, st);
     } else if (bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) && (q_packed != nullptr || q_unpacked != nullptr) &&
-               col_scale != nullptr && tma_path_enabled() && (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0 &&
+               col_scale != nullptr && (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0 &&
                group_quant_tma_cs_eligible(C, K)) {
       // K1 v2 CS: the same kernel walking column slabs, per-input-channel scales in registers (final AWQ pass)
       rc = launch_group_quant_tma_cs(w, dtype, C, K, group_size, sym, col_scale, q_packed, q_unpacked, scales_f16, zp,

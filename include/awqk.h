@@ -129,8 +129,9 @@ AWQK_API int awqk_bf16_to_fp16(const void* in_bf16, void* out_fp16, int64_t n, v
  *   q_unpacked / q_packed / scales_f16 / zp / zp_packed: outputs of the final pass, exactly as in
  *              awqk_group_quant(..., arith = FP32, col_scale = best_s); scales_f16 == NULL skips the final pass.
  *   workspace  device memory, 256-byte aligned, >= the minimum of awqk_workspace_bytes (the preferred size
- *              lets the delta producers run further ahead of the GEMM).  Must not be shared by two searches
- *              that may run at the same time.
+ *              gives the panel ring one more panel of lookahead where that helps).  Must not be shared by two
+ *              searches that may run at the same time.  The sizes depend on the CURRENT device (number of
+ *              co-resident CTA pairs): query them with the device of `w` current.
  *   Requires group_size in {32,64,128}, K % group_size == 0, K % 64 == 0, 16-byte aligned bases.
  * Inside: the score kernel is ONE persistent launch in which producer warps compute the dW operand of the
  * tensor-core GEMM tile by tile (awqk_search_fused.cu); the argmin, the winning scale vector and the final
@@ -140,8 +141,9 @@ AWQK_API int awqk_scale_search(const void* w, int dtype, int64_t C, int64_t K, c
                       double* err_mean, int32_t* best_idx, float* best_s, int32_t* q_unpacked,
                       uint32_t* q_packed, void* scales_f16, int32_t* zp, uint32_t* zp_packed,
                       void* workspace, size_t workspace_bytes, void* stream);
-/* preferred workspace size of awqk_scale_search for this problem; *minimum (nullable) gets the smallest
- * size it accepts.  have_s_grid != 0: the caller passes s_grid.  0 on bad arguments. */
+/* preferred workspace size of awqk_scale_search for this problem on the current device; *minimum (nullable) gets
+ * the smallest size it accepts.  have_s_grid != 0: the caller passes s_grid.  0 on bad arguments or without a
+ * usable device.  (A few tens of MB: counters + a ring of 2-3 panels of 256 x 2048 bf16 per slab in flight.) */
 AWQK_API size_t awqk_workspace_bytes(int64_t C, int64_t K, int64_t T, int n_grid, int have_s_grid, size_t* minimum);
 
 /* ---- the stages of the search as separate calls (tests, tools) ---- */

@@ -225,3 +225,69 @@ def test_streamed_model_search_many_waves(native_lib, cuda_device):
             assert int(out[n]["best_idx"]) == int(single["best_idx"]), (n, wave_bytes)
             assert_quant_equal(out[n], single, f"{n}/{wave_bytes}", keys=("scales", "zero_points", "qweight", "qzeros"))
             assert out[n]["qweight"].device.type == "cpu" and out[n]["qweight"].is_pinned() == pin
+
+
+def test_model_level_search_failure_modes(native_lib, cuda_device, monkeypatch):
+    """quantize_model(activations=...): (1) keep_unpacked reaches the tensors WITHOUT activations too; (2) when the
+    streamed search fails as a whole, every tensor is still searched (one by one) instead of silently losing its AWQ
+    scaling; (3) a pipelined section that fails is drained and its tensors take the per-tensor path"""
+    from awq_quantizer.quantization import AWQQuantizer
+    from awq_quantizer.quantization import arena as A
+    from awq_quantizer.quantization import stream as S
+    import awq_quantizer.quantization.search as SE
+    qz = AWQQuantizer(bits=4, group_size=128, symmetric=False, device="cuda:0", logger_level="CRITICAL", n_grid=6)
+    X = datagen.activations(96, 1024, "bf16", 9)
+    tensors = {"a": datagen.weights((256, 1024), "bf16", 1), "b": datagen.weights((128, 1024), "bf16", 2),
+               "emb": datagen.weights((64, 1024), "bf16", 3), "norm": datagen.weights((1024,), "bf16", 4)}
+    acts = {"a": X, "b": X}
+    good = qz.quantize_model(tensors, activations=acts, pack=True, keep_unpacked=True)
+    assert list(good) == list(tensors)
+    for n in tensors:                                                # (1) one schema for all tensors
+        assert {"tensor_q", "zero_points", "qweight", "qzeros", "scales"} <= set(good[n]), n
+    assert "awq_scale" in good["a"] and "awq_scale" not in good["emb"]
+    want = O.pack_result(O.group_quant_vec(tensors["emb"], 4, 128, False, True))
+    assert torch.equal(good["emb"]["qweight"], want["qweight"]) and torch.equal(good["emb"]["tensor_q"], want["tensor_q"])
+
+    def boom(*a, **k):
+        raise RuntimeError("injected failure of the streamed search")
+    monkeypatch.setattr(SE, "quantize_model_with_search", boom)      # (2)
+    fb = qz.quantize_model(tensors, activations=acts, pack=True, keep_unpacked=True)
+    monkeypatch.undo()
+    for n in ("a", "b"):
+        assert int(fb[n]["best_idx"]) == int(good[n]["best_idx"]) and torch.equal(fb[n]["qweight"], good[n]["qweight"])
+        assert torch.equal(fb[n]["awq_scale"], good[n]["awq_scale"])
+    assert torch.equal(fb["emb"]["qweight"], good["emb"]["qweight"])
+
+    calls = {"n": 0}
+    real = A.quantize_arena
+
+    def flaky(*a, **k):                                              # (3) the arena section fails once
+        calls["n"] += 1
+        if calls["n"] == 1:
+            raise RuntimeError("injected failure of the arena pipeline")
+        return real(*a, **k)
+    monkeypatch.setattr(A, "quantize_arena", flaky)
+    plain = {n: t for n, t in tensors.items()}
+    res = qz.quantize_model(plain, pack=True)
+    monkeypatch.undo()
+    assert calls["n"] >= 1 and list(sorted(res)) == sorted(plain)
+    for n, t in plain.items():
+        w = O.pack_result(O.group_quant_vec(t, 4, 128, False, True))
+        assert torch.equal(res[n]["qweight"], w["qweight"]) and torch.equal(res[n]["qzeros"], w["qzeros"]), n
+
+
+def test_search_from_worker_threads(native_lib, cuda_device):
+    """the reference calls quantize() from a ThreadPoolExecutor (main.py:609-621): concurrent searches (each with its
+    own workspace; the cooperative launches serialise on the device) give the results of sequential calls"""
+    from concurrent.futures import ThreadPoolExecutor
+    from awq_quantizer.quantization import AWQQuantizer
+    qz = AWQQuantizer(bits=4, group_size=128, symmetric=False, device="cuda:0", logger_level="ERROR", n_grid=8)
+    jobs = [(datagen.weights((256 + 64 * i, 1024), "bf16", 30 + i), datagen.activations(128, 1024, "bf16", 40 + (i % 2)))
+            for i in range(6)]
+    want = [qz.quantize(w, activations=x, pack=True) for w, x in jobs]
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        got = list(ex.map(lambda wx: qz.quantize(wx[0], activations=wx[1], pack=True), jobs))
+    for g, w in zip(got, want):
+        assert int(g["best_idx"]) == int(w["best_idx"])
+        assert torch.equal(g["qweight"], w["qweight"]) and torch.equal(g["qzeros"], w["qzeros"])
+        assert torch.allclose(g["search_err"], w["search_err"], rtol=1e-9, atol=0)

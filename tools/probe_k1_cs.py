@@ -1,5 +1,5 @@
-"""Timing probe for the column-scaled (final AWQ) K1 pass: slab kernel vs the register path
-(AWQK_FORCE_V1=1 in the environment selects the latter).  CUDA events, 2 rotating inputs > L2."""
+"""Timing probe for the column-scaled (final AWQ) K1 pass (column-slab mode of the TMA kernel).  CUDA events,
+2 rotating inputs > L2."""
 import json
 import os
 import sys
@@ -13,7 +13,7 @@ L = N.lib()
 dev = torch.device("cuda:0")
 st = torch.cuda.current_stream(dev).cuda_stream
 iters = int(os.environ.get("ITERS", "20"))
-tag = "register path" if os.environ.get("AWQK_FORCE_V1") == "1" else "slab kernel"
+tag = "slab kernel"
 
 
 def timeit(fn, iters=iters, warm=3):
