@@ -27,6 +27,7 @@ SIGNATURES = {
     "awqk_group_quant": (_int, [_vp, _int, _i64, _i64, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp,
                                 _vp, _vp]),
     "awqk_group_quant_path": (_int, [_int, _i64, _i64, _int, _int, _int, _vp]),
+    "awqk_group_quant_batch": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp]),
     "awqk_dequant": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp, _vp]),
     "awqk_dequant_packed": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
     "awqk_bf16_to_fp16": (_int, [_vp, _vp, _i64, _vp]),
@@ -48,6 +49,12 @@ SIGNATURES = {
     "awqk_host_copy": (_int, [_vp, _vp, C.c_size_t, _int]),
     "awqk_pipe_sync": (_int, [_vp]),
 }
+
+
+class QuantItem(C.Structure):
+    """awqk_quant_item of include/awqk.h"""
+    _fields_ = [("w", _vp), ("C", _i64), ("K", _i64), ("col_scale", _vp), ("q_unpacked", _vp), ("q_packed", _vp),
+                ("scales_f16", _vp), ("zp", _vp), ("zp_packed", _vp)]
 
 
 class NativeError(RuntimeError):
@@ -116,3 +123,16 @@ def host_copy(dst, src) -> None:
         dst.copy_(src)
         return
     check(lib().awqk_host_copy(dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), 0), "awqk_host_copy")
+
+
+def group_quant_batch(items, dtype_code_: int, group_size: int, bits: int, symmetric: bool, arith: int, stream) -> None:
+    """awqk_group_quant_batch over `items` = [(w, C, K, col_scale, q_unpacked, q_packed, scales, zp, zp_packed)] of
+    tensors / None: the K1 pass of a whole wave of tensors in as few launches as possible."""
+    if not items:
+        return
+    arr = (QuantItem * len(items))()
+    for a, (w, Cc, K, cs, qu, qp, sc, zp, zq) in zip(arr, items):
+        a.w, a.C, a.K, a.col_scale = w.data_ptr(), Cc, K, ptr(cs)
+        a.q_unpacked, a.q_packed, a.scales_f16, a.zp, a.zp_packed = ptr(qu), ptr(qp), sc.data_ptr(), ptr(zp), ptr(zq)
+    check(lib().awqk_group_quant_batch(C.cast(arr, _vp), len(items), dtype_code_, group_size, bits, int(symmetric), arith,
+                                       stream), "awqk_group_quant_batch")

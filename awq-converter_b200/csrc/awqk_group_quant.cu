@@ -457,6 +457,17 @@ bool group_quant_tma_cs_eligible(int64_t C, int64_t K);
 int launch_group_quant_tma_cs(const void* w, int dtype, int64_t C, int64_t K, int g, bool sym, const float* col_scale,
                               uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                               cudaStream_t st);
+int launch_group_quant_tma_cs_batch(const awqk_quant_item* items, int n, int dtype, int g, bool sym, cudaStream_t st);
+constexpr int kCsMaxBatch = 31;   // = kV2MaxTensors
+
+// does awqk_group_quant send this call to the column-slab kernel?
+static bool cs_path(int dtype, int64_t C, int64_t K, int group_size, int bits, int arith, const void* w,
+                    const uint32_t* q_packed, const int32_t* q_unpacked, const float* col_scale) {
+  return bits == 4 && arith == AWQK_ARITH_FP32 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) &&
+         (q_packed != nullptr || q_unpacked != nullptr) && col_scale != nullptr &&
+         (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0 && flat_eligible(dtype, K, group_size, w) &&
+         group_quant_tma_cs_eligible(C, K);
+}
 
 }  // namespace awqk
 
@@ -511,10 +522,8 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
       // K1 v2: TMA-staged, packed-math kernel (int4 pack path and the reference's int32 code layout)
       rc = launch_group_quant_tma(w, dtype, n, group_size, bits, sym, arith, q_packed, q_unpacked, scales_f16, zp,
                                   out.zp_packed, zq_log2, st);
-    } else if (bits == 4 && (dtype == AWQK_BF16 || dtype == AWQK_FP16) && (q_packed != nullptr || q_unpacked != nullptr) &&
-               col_scale != nullptr && (reinterpret_cast<uintptr_t>(q_packed) & 15u) == 0 &&
-               group_quant_tma_cs_eligible(C, K)) {
-      // K1 v2 CS: the same kernel walking column slabs, per-input-channel scales in registers (final AWQ pass)
+    } else if (cs_path(dtype, C, K, group_size, bits, arith, w, q_packed, q_unpacked, col_scale)) {
+      // K1 v2 CS: column-slab kernel, per-input-channel scales in a shared-memory table (final AWQ pass)
       rc = launch_group_quant_tma_cs(w, dtype, C, K, group_size, sym, col_scale, q_packed, q_unpacked, scales_f16, zp,
                                      out.zp_packed, st);
     } else
@@ -569,4 +578,48 @@ extern "C" int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, 
   }
   return launch_generic<float, AR_F32>(reinterpret_cast<const float*>(w), C, K, group_size, G, bits, sym,
                                        col_scale, out, st);
+}
+
+extern "C" int awqk_group_quant_batch(const awqk_quant_item* items, int n_items, int dtype, int group_size, int bits,
+                                      int symmetric, int arith, void* stream) {
+  if (n_items < 0 || (n_items > 0 && items == nullptr)) return AWQK_E_BADARG;
+  if (n_items == 0) return AWQK_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // one launch holds tensors with the same set of outputs: bucket = (int32 codes, zp, zp_packed, q_packed)
+  awqk_quant_item batch[16][kCsMaxBatch];
+  int fill[16] = {0};
+  DeviceGuard guard(items[0].w);
+  if (guard.status != AWQK_OK) return guard.status;
+  auto flush = [&](int k) -> int {
+    if (fill[k] == 0) return AWQK_OK;
+    const int rc = launch_group_quant_tma_cs_batch(batch[k], fill[k], dtype, group_size, symmetric != 0, st);
+    fill[k] = 0;
+    return rc;
+  };
+  for (int i = 0; i < n_items; ++i) {
+    const awqk_quant_item& it = items[i];
+    if (it.w == nullptr || it.scales_f16 == nullptr) return AWQK_E_BADARG;
+    const int path = awqk_group_quant_path(dtype, it.C, it.K, group_size, bits, arith, it.w);
+    if (path < 0) return path;
+    const bool aligned = !(it.q_unpacked && (reinterpret_cast<uintptr_t>(it.q_unpacked) & 15u)) &&
+                         !(it.col_scale && (reinterpret_cast<uintptr_t>(it.col_scale) & 15u));
+    if (path == 1 && aligned &&
+        cs_path(dtype, it.C, it.K, group_size, bits, arith, it.w, it.q_packed, it.q_unpacked, it.col_scale)) {
+      const int k = (it.q_unpacked ? 1 : 0) | (it.zp ? 2 : 0) | (it.zp_packed ? 4 : 0) | (it.q_packed ? 8 : 0);
+      batch[k][fill[k]++] = it;
+      if (fill[k] == kCsMaxBatch) {
+        const int rc = flush(k);
+        if (rc != AWQK_OK) return rc;
+      }
+      continue;
+    }
+    const int rc = awqk_group_quant(it.w, dtype, it.C, it.K, group_size, bits, symmetric, arith, it.q_unpacked, it.q_packed,
+                                    it.scales_f16, it.zp, it.zp_packed, it.col_scale, stream);
+    if (rc != AWQK_OK) return rc;
+  }
+  for (int k = 0; k < 16; ++k) {
+    const int rc = flush(k);
+    if (rc != AWQK_OK) return rc;
+  }
+  return AWQK_OK;
 }

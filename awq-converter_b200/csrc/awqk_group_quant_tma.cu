@@ -15,6 +15,7 @@
 //     nibble merge by one IMAD per pair + 3 PRMT per word.
 // A warp tile is 1024 elements = 8/16/32 groups, i.e. a whole number of packed zero-point words.
 #include <atomic>
+#include <cstring>
 
 #include "awqk_common.cuh"
 
@@ -133,6 +134,19 @@ struct PairQuant<AR_F32, QMIN, BITS> {
     const uint32_t both = __byte_perm(__float_as_uint(t.x), __float_as_uint(t.y), 0x5410);
     return __vimin_s16x2_relu(both, (uint32_t)((1 << BITS) - 1) * 0x00010001u);
   }
+  // int4: 8 quotients (elements 0..7 = q[0].x, q[0].y, q[1].x, ...) -> one packed word.  Element j is paired with
+  // element j + 4 (low / high s16 lane), so the clamped pair r_j only has to move left by 4j bits: the nibble merge
+  // is 3 IMADs, no byte gather.  sel = 0x5410, or 0x1054 to swap the two halves of the word (fp32 input, odd lanes).
+  __device__ __forceinline__ uint32_t pack8(const float2 (&q)[4], uint32_t sel) const {
+    float2 t[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) t[p] = __fadd2_rn(__fadd2_rn(q[p], zp2), magic2);
+    const uint32_t r0 = __vimin_s16x2_relu(__byte_perm(__float_as_uint(t[0].x), __float_as_uint(t[2].x), sel), 0x000F000Fu);
+    const uint32_t r1 = __vimin_s16x2_relu(__byte_perm(__float_as_uint(t[0].y), __float_as_uint(t[2].y), sel), 0x000F000Fu);
+    const uint32_t r2 = __vimin_s16x2_relu(__byte_perm(__float_as_uint(t[1].x), __float_as_uint(t[3].x), sel), 0x000F000Fu);
+    const uint32_t r3 = __vimin_s16x2_relu(__byte_perm(__float_as_uint(t[1].y), __float_as_uint(t[3].y), sel), 0x000F000Fu);
+    return (r3 * 16u + r2) * 256u + (r1 * 16u + r0);
+  }
 };
 template <int QMIN>
 struct PairQuant<AR_BF16, QMIN, 4> {
@@ -149,6 +163,14 @@ struct PairQuant<AR_BF16, QMIN, 4> {
     const __nv_bfloat162 a = __float22bfloat162_rn(q);
     const __nv_bfloat162 t = __hadd2(__hadd2(a, zp2), magic2);
     return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), rebase, 0x000F000Fu);
+  }
+  __device__ __forceinline__ uint32_t pair(float lo, float hi) const {
+    const __nv_bfloat162 t = __hadd2(__hadd2(__floats2bfloat162_rn(lo, hi), zp2), magic2);
+    return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), rebase, 0x000F000Fu);
+  }
+  __device__ __forceinline__ uint32_t pack8(const float2 (&q)[4], uint32_t) const {   // (see PairQuant<AR_F32>)
+    const uint32_t r0 = pair(q[0].x, q[2].x), r1 = pair(q[0].y, q[2].y), r2 = pair(q[1].x, q[3].x), r3 = pair(q[1].y, q[3].y);
+    return (r3 * 16u + r2) * 256u + (r1 * 16u + r0);
   }
 };
 template <int QMIN>
@@ -167,6 +189,14 @@ struct PairQuant<AR_F16, QMIN, 4> {
     const __half2 t = __hadd2(__hadd2(a, zp2), magic2);
     return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), rebase, 0x000F000Fu);
   }
+  __device__ __forceinline__ uint32_t pair(float lo, float hi) const {
+    const __half2 t = __hadd2(__hadd2(__floats2half2_rn(lo, hi), zp2), magic2);
+    return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), rebase, 0x000F000Fu);
+  }
+  __device__ __forceinline__ uint32_t pack8(const float2 (&q)[4], uint32_t) const {
+    const uint32_t r0 = pair(q[0].x, q[2].x), r1 = pair(q[0].y, q[2].y), r2 = pair(q[1].x, q[3].x), r3 = pair(q[1].y, q[3].y);
+    return (r3 * 16u + r2) * 256u + (r1 * 16u + r0);
+  }
 };
 
 // 8 bit in the reference's bf16 / fp16 arithmetic: a = A(q), b = A(a + zp) as above, but codes up to 255 leave
@@ -174,6 +204,7 @@ struct PairQuant<AR_F16, QMIN, 4> {
 // fp32 magic instead (rint of an A-representable value is the same number in either format).
 template <int QMIN>
 struct PairQuant<AR_BF16, QMIN, 8> {
+  __device__ __forceinline__ uint32_t pack8(const float2 (&)[4], uint32_t) const { return 0u; }   // int4 only
   __nv_bfloat162 zp2;
   float2 magic2;
   __device__ __forceinline__ void prepare() { magic2 = make_float2(12582912.0f - (float)QMIN, 12582912.0f - (float)QMIN); }
@@ -188,6 +219,7 @@ struct PairQuant<AR_BF16, QMIN, 8> {
 };
 template <int QMIN>
 struct PairQuant<AR_F16, QMIN, 8> {
+  __device__ __forceinline__ uint32_t pack8(const float2 (&)[4], uint32_t) const { return 0u; }   // int4 only
   __half2 zp2;
   float2 magic2;
   __device__ __forceinline__ void prepare() { magic2 = make_float2(12582912.0f - (float)QMIN, 12582912.0f - (float)QMIN); }
@@ -216,20 +248,6 @@ struct V2Out {
 // directions conflict-free) and stores 512 contiguous bytes per instruction.
 constexpr int kV2UnpStageBytes = kV2ConsumerWarps * kV2WarpTile * 4;   // 32 KiB per CTA
 
-// CS ("column scaled", the final AWQ pass: quantize fp32(w) * s[k], awqk.h col_scale): the tensor is cut
-// into column slabs of 1024 (one warp tile wide); a CTA owns ONE slab and walks down it 8 rows per stage
-// (8 bulk copies of 2 KiB, one per consumer warp), so a thread's 32 columns never change and their
-// scales live in registers for the whole kernel.  Requires K % 1024 == 0: every output offset is then
-// still (thread base) + it * (constant stride) in the flat row-major arrays, exactly as in the flat mode.
-// The cps CTAs of a slab take row blocks j, j + cps, ...: all slabs sweep the same rows at the same time,
-// which keeps the HBM pages of a row open (a contiguous, perfectly balanced split of the row blocks per
-// CTA measured 3-8 % slower for that reason).
-struct V2ColScale {
-  const float* s;     // [K]
-  int64_t K, C;
-  int n_slabs, cps;   // K / 1024, CTAs per slab (grid = n_slabs * cps)
-};
-
 __device__ __forceinline__ float fmin3_nan(float a, float b, float c) {
   float r;
   asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -241,192 +259,58 @@ __device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
   return r;
 }
 
+// One consumer thread of K1 v2: its invariants and the work on one warp tile (32 consecutive elements per
+// thread, already in registers).  Shared by the flat kernel and the column-slab kernel below.
+//   CS: x = fp32(w) * s[k] with the thread's 32 column scales read from a shared-memory table laid out
+//   [chunk j = 0..7][lane] x 16 B (conflict-free LDS.128 at immediate offsets j * 512 from `cs_thr`).
 template <typename InT, int A, int G, bool SYM, bool UNPACKED, bool CS, int BITS>
-__global__ void __launch_bounds__(kV2Threads, (UNPACKED || sizeof(InT) == 4) ? 2 : 3)
-group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out, V2ColScale csp) {
-  static_assert(!CS || A == AR_F32, "column scaling is defined in fp32 arithmetic");
-  static_assert(BITS == 4 || BITS == 8, "int4 or int8 codes");
-  // fp32 input: a thread's 32 elements are 128 B = 8 LDS.128; stages are 32 KiB, so 3 of them (2 with the
-  // UNPACKED staging) keep 2 CTAs per SM.  Chunk c of the thread's span is read into slot c ^ (lane & 7)
-  // (conflict-free: a quarter warp covers all 8 bank groups); slots 2w, 2w+1 still hold the two halves of one
-  // packed word, swapped for odd lanes.
-  constexpr bool F32IN = sizeof(InT) == 4;
-  static_assert(!F32IN || (A == AR_F32 && !CS && BITS == 4), "fp32 input: fp32 arithmetic, flat mode, int4");
-  constexpr int STAGES = F32IN ? (UNPACKED ? 2 : 3) : kV2Stages;
-  constexpr uint32_t STAGE_BYTES = kV2CtaTile * sizeof(InT);
-  constexpr int NW = BITS;               // packed words per thread: 32 codes * BITS / 32
-  constexpr uint32_t CMAX = (1u << BITS) - 1u;
-  constexpr int LPG = G / 32;            // lanes per group (4, 2, 1)
-  const int LPW = LPG << out.zq_log2;    // lanes per packed zero-point word (8 groups: 32, 16, 8)
-  constexpr int QMIN = SYM ? -(1 << (BITS - 1)) : 0;
-  constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + (int)CMAX);
+struct V2Consumer {
+  static constexpr bool F32IN = sizeof(InT) == 4;
+  static constexpr int NLD = F32IN ? 8 : 4;                // LDS.128 per thread and tile
+  static constexpr int NW = BITS;                          // packed words per thread: 32 codes * BITS / 32
+  static constexpr uint32_t CMAX = (1u << BITS) - 1u;
+  static constexpr int LPG = G / 32;                       // lanes per group (4, 2, 1)
+  static constexpr int QMIN = SYM ? -(1 << (BITS - 1)) : 0;
+  static constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + (int)CMAX);
 
-  extern __shared__ __align__(128) uint8_t smem[];
-  // CS: the slab's 1024 fp32 column scales, one 128-byte row per lane (all 8 consumer warps walk the same columns),
-  // chunk (2c + h) of a lane stored at position (2c + h) ^ (lane & 7): conflict-free LDS.128 for every quarter warp
-  constexpr uint32_t CS_BYTES = CS ? kV2WarpTile * 4 : 0;
-  const uint32_t cs_sm = smem_u32(smem) + STAGES * STAGE_BYTES + (UNPACKED ? kV2UnpStageBytes : 0);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (UNPACKED ? kV2UnpStageBytes : 0) + CS_BYTES);
-  uint32_t full0 = smem_u32(bars);
-  uint32_t empty0 = smem_u32(bars + STAGES);
-  asm volatile("" : "+r"(full0), "+r"(empty0));   // keep the shared-window addresses in registers
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, kV2ConsumerWarps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (CS && warp == 0) {                         // lane l: its 32 scales, in the rotated chunk order of the W loads
-    const int rot0 = (lane >> 1) & 3;
-    const float* sp0 = csp.s + (int64_t)(blockIdx.x % (unsigned)csp.n_slabs) * kV2WarpTile + lane * 32;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(sp0 + 8 * ((c + rot0) & 3) + 4 * h));
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cs_sm + (uint32_t)lane * 128u +
-                                                                     (uint32_t)(((2 * c + h) ^ (lane & 7)) << 4)),
-                     "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                     : "memory");
-      }
-    }
-  }
-  __syncthreads();
-
-  // flat: CTA b takes tiles b, b + grid, ...   CS: CTA b takes row blocks j, j + cps, ... of slab b % n_slabs
-  const int64_t tile0 = CS ? (int64_t)(blockIdx.x / (unsigned)csp.n_slabs) : (int64_t)blockIdx.x;
-  const int64_t tile_step = CS ? (int64_t)csp.cps : (int64_t)gridDim.x;
-  const int64_t n_iters = (n_tiles > tile0) ? (n_tiles - tile0 + tile_step - 1) / tile_step : 0;
-  const int64_t slab_col = CS ? (int64_t)(blockIdx.x % (unsigned)csp.n_slabs) * kV2WarpTile : 0;
-
-  if (warp == kV2ConsumerWarps) {
-    // ================= producer: one thread streams CTA tiles into the ring =================
-    if (CS) {
-      if (lane == 0) {
-        const int64_t row_bytes = csp.K * 2;
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(w) + (tile0 * kV2ConsumerWarps) * row_bytes + slab_col * 2;
-        const int64_t src_stride = tile_step * kV2ConsumerWarps * row_bytes;
-        int64_t rows_left = csp.C - tile0 * kV2ConsumerWarps;
-        uint32_t stage = 0, ph = 1;
-        for (int64_t it = 0; it < n_iters; ++it) {
-          mbar_wait(empty0 + 8 * stage, ph);
-          const int rows = rows_left < kV2ConsumerWarps ? (int)rows_left : kV2ConsumerWarps;
-          mbar_expect_tx(full0 + 8 * stage, (uint32_t)rows * (kV2WarpTile * 2));
-          const uint32_t dst = smem_u32(smem) + stage * STAGE_BYTES;
-          for (int r = 0; r < rows; ++r)
-            bulk_g2s(dst + r * (kV2WarpTile * 2), src + r * row_bytes, kV2WarpTile * 2, full0 + 8 * stage);
-          src += src_stride;
-          rows_left -= tile_step * kV2ConsumerWarps;
-          if (++stage == STAGES) { stage = 0; ph ^= 1u; }
-        }
-      }
-      return;
-    }
-    if (lane == 0) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(w) + tile0 * STAGE_BYTES;
-      const int64_t src_stride = (int64_t)gridDim.x * STAGE_BYTES;
-      int64_t left = n_elems * (int64_t)sizeof(InT) - tile0 * STAGE_BYTES;          // bytes from this tile to the end
-      uint32_t stage = 0, ph = 1;                                   // first pass over the ring: slots are free
-      for (int64_t it = 0; it < n_iters; ++it) {
-        mbar_wait(empty0 + 8 * stage, ph);
-        const uint32_t bytes = (left < STAGE_BYTES) ? (uint32_t)left : (uint32_t)STAGE_BYTES;
-        mbar_expect_tx(full0 + 8 * stage, bytes);
-        bulk_g2s(smem_u32(smem) + stage * STAGE_BYTES, src, bytes, full0 + 8 * stage);
-        src += src_stride;
-        left -= src_stride;
-        if (++stage == STAGES) { stage = 0; ph ^= 1u; }
-      }
-    }
-    return;
-  }
-
-  // ================================ consumers =================================================
-  // per-thread invariants.  Output addresses are (thread base) + it * (byte stride): one IMAD.WIDE
-  // per store, no loop-carried 64-bit pointers.
-  const int64_t warp_e_first = CS ? (tile0 * kV2ConsumerWarps + warp) * csp.K + slab_col
-                                  : tile0 * kV2CtaTile + (int64_t)warp * kV2WarpTile;
-  const int64_t e_first = warp_e_first + (int64_t)lane * 32;
-  const int64_t e_stride = CS ? tile_step * kV2ConsumerWarps * csp.K : tile_step * kV2CtaTile;
-  const uint32_t iters = (uint32_t)n_iters;
-  // iterations in which this thread's 32 elements exist (whole groups are valid or not)
-  const uint32_t valid_iters = (n_elems > e_first) ? (uint32_t)((n_elems - e_first + e_stride - 1) / e_stride) : 0u;
-  // rot: bf16/fp16 -> slot c holds chunk (c + rot) & 3; fp32 -> word slot wp holds word wp ^ rot
-  const int rot = (lane >> 1) & 3;
-  const uint32_t smem_thr = smem_u32(smem) + (uint32_t)warp * (kV2WarpTile * (uint32_t)sizeof(InT)) +
-                            (uint32_t)lane * (32u * (uint32_t)sizeof(InT));
-  constexpr int NLD = F32IN ? 8 : 4;                // LDS.128 per thread and tile
-  uint32_t ld_off[NLD];
-#pragma unroll
-  for (int c = 0; c < NLD; ++c) {
-    ld_off[c] = smem_thr + (uint32_t)((F32IN ? (c ^ (lane & 7)) : ((c + rot) & 3)) << 4);
-    asm volatile("" : "+r"(ld_off[c]));             // (no per-tile re-derivation from SR_CgaCtaId)
-  }
-  // fp32 input: half-word merge selector (even lanes: slot 2w is the low half of word w; odd lanes: the high half)
-  const uint32_t half_sel = (F32IN && (lane & 1)) ? 0x1054u : 0x5410u;
-  const int odd_shift = (F32IN && (lane & 1)) ? 2 : 0;
-  uint8_t* const q_base = reinterpret_cast<uint8_t*>(out.q_packed) + e_first * BITS / 8;
-  uint8_t* const s_base = reinterpret_cast<uint8_t*>(out.scales + e_first / G);
-  uint8_t* const z_base = reinterpret_cast<uint8_t*>(out.zp + e_first / G);
-  uint8_t* const zq_base = reinterpret_cast<uint8_t*>(out.zp_packed + ((e_first / G) >> out.zq_log2));
-  const uint32_t q_step = (uint32_t)(e_stride * BITS / 8);         // bytes per iteration (< 2^32: grid <= 3*SMs)
-  const uint32_t s_step = (uint32_t)(e_stride / G) * 2u;
-  const uint32_t z_step = (uint32_t)(e_stride / G) * 4u;
-  const uint32_t zq_step = (uint32_t)((e_stride / G) >> out.zq_log2) * 4u;
-  const bool has_zp = out.zp != nullptr, has_zq = out.zp_packed != nullptr;
-  const bool leader = (lane % LPG) == 0;
-  const bool zq_writer = (lane & (LPW - 1)) == 0;
-  const uint32_t zq_shift = (uint32_t)BITS * ((uint32_t)(lane / LPG) & ((1u << out.zq_log2) - 1u));
-  const uint32_t zq_mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
-
-  // UNPACKED: warp-private staging of 256 x 16 B chunks.  Thread l owns logical chunks 8l..8l+7 (4 codes
-  // each); chunk j is stored at 8l + (j ^ (l & 7)); store instruction t reads logical chunk 32t + l.
+  int lane, rot, odd_shift, LPW;
+  uint32_t half_sel, zq_shift, zq_mask;
+  bool leader, zq_writer;
   uint32_t stg_w[8], stg_r[8];
-  uint8_t* qu_base = nullptr;
-  const bool has_qp = out.q_packed != nullptr;
-  if (UNPACKED) {
-    const uint32_t stg0 = smem_u32(smem) + STAGES * STAGE_BYTES + (uint32_t)warp * (kV2WarpTile * 4);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      stg_w[j] = stg0 + (uint32_t)((8 * lane + (j ^ (lane & 7))) << 4);
-      const int o = 4 * j + (lane >> 3);                       // owner lane of logical chunk 32j + lane
-      stg_r[j] = stg0 + (uint32_t)((8 * o + ((lane & 7) ^ (o & 7))) << 4);
-    }
-    // this lane's first coalesced chunk of the warp tile: element 4 * lane
-    qu_base = reinterpret_cast<uint8_t*>(out.q_unpacked + warp_e_first + 4 * lane);
-  }
-  const uint32_t qu_step = (uint32_t)e_stride * 4u;              // bytes per iteration (host keeps it < 2^32)
-  // CS: this lane's row of the column-scale table (read chunk by chunk inside the loop: 8 more LDS.128 per tile
-  // instead of 32 registers for the whole kernel -> 3 CTAs per SM like the flat mode)
-  const uint32_t cs_thr = cs_sm + (uint32_t)lane * 128u;
-  const uint32_t cs_x = (uint32_t)(lane & 7);
-
   PairQuant<A, QMIN, BITS> pq;
-  pq.prepare();
-  uint32_t stage = 0, ph = 0;
-  for (uint32_t it = 0; it < iters; ++it) {
-    const bool valid = it < valid_iters;
-    mbar_wait(full0 + 8 * stage, ph);
-    // 64 B per thread as 4 x LDS.128.  Register slot c holds 16-byte chunk (c + rot) & 3 of the
-    // thread's span: rotating the chunk order by lane/2 makes every quarter-warp hit 8 distinct
-    // bank groups.  Min/max and the per-word quantization are order independent; only the final
-    // 16-byte store has to rotate the 4 result words back (8 SELs).
-    uint32_t wds[4 * NLD];
-#pragma unroll
-    for (int c = 0; c < NLD; ++c) {
-      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(wds[4 * c]), "=r"(wds[4 * c + 1]), "=r"(wds[4 * c + 2]), "=r"(wds[4 * c + 3])
-                   : "r"(ld_off[c] + stage * STAGE_BYTES));
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty0 + 8 * stage);   // slot is free as soon as it sits in registers
-    if (++stage == STAGES) { stage = 0; ph ^= 1u; }
-    // (threads past the end of the tensor compute on stale shared memory and store nothing)
 
+  // stg0: this warp's 4 KiB of the UNPACKED staging area (shared-window address)
+  __device__ __forceinline__ void init(int lane_, int zq_log2, uint32_t stg0) {
+    lane = lane_;
+    // rot: bf16/fp16 -> slot c holds chunk (c + rot) & 3; fp32 -> word slot wp holds word wp ^ rot
+    rot = (lane >> 1) & 3;
+    LPW = LPG << zq_log2;                // lanes per packed zero-point word (8 groups: 32, 16, 8)
+    // fp32 input: half-word merge selector (even lanes: slot 2w is the low half of word w; odd lanes: the high half)
+    half_sel = (F32IN && (lane & 1)) ? 0x1054u : 0x5410u;
+    odd_shift = (F32IN && (lane & 1)) ? 2 : 0;
+    leader = (lane % LPG) == 0;
+    zq_writer = (lane & (LPW - 1)) == 0;
+    zq_shift = (uint32_t)BITS * ((uint32_t)(lane / LPG) & ((1u << zq_log2) - 1u));
+    zq_mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
+    // UNPACKED: warp-private staging of 256 x 16 B chunks.  Thread l owns logical chunks 8l..8l+7 (4 codes
+    // each); chunk j is stored at 8l + (j ^ (l & 7)); store instruction t reads logical chunk 32t + l.
+    if (UNPACKED) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        stg_w[j] = stg0 + (uint32_t)((8 * lane + (j ^ (lane & 7))) << 4);
+        const int o = 4 * j + (lane >> 3);                       // owner lane of logical chunk 32j + lane
+        stg_r[j] = stg0 + (uint32_t)((8 * o + ((lane & 7) ^ (o & 7))) << 4);
+      }
+    }
+    pq.prepare();
+  }
+
+  // wds: the thread's 32 elements.  valid: they exist.  *_dst: where this thread's results of this tile go
+  // (qu_dst: the lane's first coalesced 16-byte chunk of the warp tile, qu_left: int32 codes from the start of the
+  // warp tile to the end of the tensor).
+  __device__ __forceinline__ void tile(const uint32_t (&wds)[4 * NLD], uint32_t cs_thr, bool valid, uint8_t* q_dst,
+                                       uint8_t* s_dst, uint8_t* z_dst, uint8_t* zq_dst, uint8_t* qu_dst, int64_t qu_left,
+                                       bool has_qp, bool has_zp, bool has_zq) {
     // ---- group min / max: packed tree over 16 words, then fold halves, then LPG lanes --------
     float mn, mx;
     float2 xv[(CS || F32IN) ? 16 : 1];
@@ -438,7 +322,7 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
           float4 sv;
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                        : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w)
-                       : "r"(cs_thr + (((uint32_t)ch ^ cs_x) << 4)));
+                       : "r"(cs_thr + (uint32_t)ch * 512u));
           xv[2 * ch] = __fmul2_rn(Packed<InT>::to_f2(wds[(2 * ch) % (4 * NLD)]), make_float2(sv.x, sv.y));
           xv[2 * ch + 1] = __fmul2_rn(Packed<InT>::to_f2(wds[(2 * ch + 1) % (4 * NLD)]), make_float2(sv.z, sv.w));
         }
@@ -474,7 +358,8 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     }
 
     const FastGroup fg = group_params_fast<A, BITS>(mn, mx, SYM, FQMIN, FQMAX);
-    float sc = fg.scale, zp = fg.zp;
+    float sc = fg.scale;
+    int zi;                          // the zero point as the reference's int32 (NaN -> INT32_MIN: slow path only)
     uint32_t words[NW];              // BITS = 4: slot wi -> words[wi]; BITS = 8: slot wi -> words[2 wi], words[2 wi + 1]
     uint32_t nanmask = 0;            // UNPACKED: bit e <=> code of logical element e is NaN (INT32_MIN)
     // tighter than group_params_fast: the packed 16-bit clamp needs round(x/s + zp) inside the
@@ -486,34 +371,32 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     constexpr float LIM = (A == AR_F32 || BITS == 8) ? 16384.0f : ((A == AR_BF16) ? 48.0f : 400.0f);
     const bool fast = fg.ok && (fmaxf(fabsf(mn), fabsf(mx)) < sc * LIM);
     if (fast) {
-      pq.init(zp);
+      pq.init(fg.zp);
+      zi = __float2int_rz(fg.zp);
       const float2 r2 = make_float2(fg.rcp, fg.rcp);
       const float2 ns2 = make_float2(-sc, -sc);
 #pragma unroll
       for (int wi = 0; wi < 4; ++wi) {
-        uint32_t b3[4];
+        float2 qv[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const float2 x = (CS || F32IN) ? xv[(CS || F32IN) ? 4 * wi + p : 0] : Packed<InT>::to_f2(wds[4 * wi + p]);
           const float2 q0 = __fmul2_rn(x, r2);
           const float2 e = __ffma2_rn(ns2, q0, x);
-          const float2 q = __ffma2_rn(e, r2, q0);                 // correctly rounded x / s
-          const uint32_t u2 = pq.run(q);                          // (u_lo | u_hi << 16)
-          b3[p] = (BITS == 4) ? u2 * 0x01001000u : u2;            // int4: byte 3 = u_lo | u_hi << 4
+          qv[p] = __ffma2_rn(e, r2, q0);                          // correctly rounded x / s
         }
         if (BITS == 4) {
-          const uint32_t lo = __byte_perm(b3[0], b3[1], 0x0073);
-          const uint32_t hi = __byte_perm(b3[2], b3[3], 0x0073);
-          words[wi * (NW / 4)] = __byte_perm(lo, hi, half_sel);
-        } else {                                                  // int8: bytes 0 and 2 of each pair
-          words[wi * (NW / 4)] = __byte_perm(b3[0], b3[1], 0x6420);
-          words[wi * (NW / 4) + (NW / 4 - 1)] = __byte_perm(b3[2], b3[3], 0x6420);
+          words[wi * (NW / 4)] = pq.pack8(qv, half_sel);
+        } else {                                                  // int8: bytes 0 and 2 of each pair (u_lo | u_hi << 16)
+          words[wi * (NW / 4)] = __byte_perm(pq.run(qv[0]), pq.run(qv[1]), 0x6420);
+          words[wi * (NW / 4) + (NW / 4 - 1)] = __byte_perm(pq.run(qv[2]), pq.run(qv[3]), 0x6420);
         }
       }
     } else {
       const GroupParams gp = group_params<A>(mn, mx, SYM, FQMIN, FQMAX);   // exact IEEE path
       sc = gp.scale;
-      zp = gp.zp;
+      const float zp = gp.zp;
+      zi = f2i_x86(zp);
 #pragma unroll
       for (int wi = 0; wi < 4; ++wi) {
         uint32_t acc = 0, acc2 = 0;
@@ -544,7 +427,6 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
     }
 
     // ---- stores ------------------------------------------------------------------------------
-    const int zi = f2i_x86(zp);
     // slot c holds chunk (c + rot) & 3  ->  chunk k sits in slot (k - rot) & 3: rotate left by rot
     // (a slot is one word for int4, two for int8: ow[h][k] = word h of chunk k)
     uint32_t ow[NW / 4][4];
@@ -560,12 +442,11 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
       ow[h][0] = o0; ow[h][1] = o1; ow[h][2] = o2; ow[h][3] = o3;
     }
     if (valid && (!UNPACKED || has_qp)) {
-      uint8_t* dst = q_base + (uint64_t)it * q_step;
       if (BITS == 4) {
-        st_stream16(dst, make_uint4(ow[0][0], ow[0][1], ow[0][2], ow[0][3]));
+        st_stream16(q_dst, make_uint4(ow[0][0], ow[0][1], ow[0][2], ow[0][3]));
       } else {
-        st_stream16(dst, make_uint4(ow[0][0], ow[NW / 4 - 1][0], ow[0][1], ow[NW / 4 - 1][1]));
-        st_stream16(dst + 16, make_uint4(ow[0][2], ow[NW / 4 - 1][2], ow[0][3], ow[NW / 4 - 1][3]));
+        st_stream16(q_dst, make_uint4(ow[0][0], ow[NW / 4 - 1][0], ow[0][1], ow[NW / 4 - 1][1]));
+        st_stream16(q_dst + 16, make_uint4(ow[0][2], ow[NW / 4 - 1][2], ow[0][3], ow[NW / 4 - 1][3]));
       }
     }
     if (UNPACKED) {
@@ -596,19 +477,17 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
       }
       __syncwarp();
       // whole 16-byte chunks are valid or not: the tensor ends on a group (>= 32 element) boundary
-      const int64_t warp_e0 = warp_e_first + (int64_t)it * e_stride;
-      uint8_t* dst = qu_base + (uint64_t)it * qu_step;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         uint4 v;
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(stg_r[t]));
-        if (warp_e0 + 128 * t + 4 * lane < n_elems) st_stream16(dst + 512 * t, v);
+        if (128 * t + 4 * lane < qu_left) st_stream16(qu_dst + 512 * t, v);
       }
       __syncwarp();                                    // staging is reused by the next tile
     }
     if (valid && leader) {
-      *reinterpret_cast<__half*>(s_base + (uint64_t)it * s_step) = __float2half_rn(sc);
-      if (has_zp) *reinterpret_cast<int32_t*>(z_base + (uint64_t)it * z_step) = zi;
+      *reinterpret_cast<__half*>(s_dst) = __float2half_rn(sc);
+      if (has_zp) *reinterpret_cast<int32_t*>(z_dst) = zi;
     }
     if (has_zq) {
       const uint32_t uz = (valid && leader && zi != INT32_MIN) ? ((uint32_t)(zi - QMIN) & CMAX) : 0u;
@@ -616,75 +495,391 @@ group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2O
       // g = 128 / int4 case packs one word per warp)
       const uint32_t wordz = (LPW == 32) ? __reduce_or_sync(0xFFFFFFFFu, uz << zq_shift)
                                          : __reduce_or_sync(zq_mask, uz << zq_shift);
-      if (valid && zq_writer) *reinterpret_cast<uint32_t*>(zq_base + (uint64_t)it * zq_step) = wordz;
+      if (valid && zq_writer) *reinterpret_cast<uint32_t*>(zq_dst) = wordz;
     }
+  }
+};
+
+// ============================================================================================================
+// flat mode: the tensor (or a whole arena of tensors) is one run of contiguous groups
+// ============================================================================================================
+template <typename InT, int A, int G, bool SYM, bool UNPACKED, int BITS>
+__global__ void __launch_bounds__(kV2Threads, (UNPACKED || sizeof(InT) == 4) ? 2 : 3)
+group_quant_tma(const InT* __restrict__ w, int64_t n_elems, int64_t n_tiles, V2Out out) {
+  static_assert(BITS == 4 || BITS == 8, "int4 or int8 codes");
+  // fp32 input: a thread's 32 elements are 128 B = 8 LDS.128; stages are 32 KiB, so 3 of them (2 with the
+  // UNPACKED staging) keep 2 CTAs per SM.  Chunk c of the thread's span is read into slot c ^ (lane & 7)
+  // (conflict-free: a quarter warp covers all 8 bank groups); slots 2w, 2w+1 still hold the two halves of one
+  // packed word, swapped for odd lanes.
+  using Cons = V2Consumer<InT, A, G, SYM, UNPACKED, false, BITS>;
+  constexpr bool F32IN = Cons::F32IN;
+  static_assert(!F32IN || (A == AR_F32 && BITS == 4), "fp32 input: fp32 arithmetic, int4");
+  constexpr int STAGES = F32IN ? (UNPACKED ? 2 : 3) : kV2Stages;
+  constexpr uint32_t STAGE_BYTES = kV2CtaTile * sizeof(InT);
+  constexpr int NLD = Cons::NLD;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (UNPACKED ? kV2UnpStageBytes : 0));
+  uint32_t full0 = smem_u32(bars);
+  uint32_t empty0 = smem_u32(bars + STAGES);
+  asm volatile("" : "+r"(full0), "+r"(empty0));   // keep the shared-window addresses in registers
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, kV2ConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // CTA b takes tiles b, b + grid, ...
+  const int64_t tile0 = (int64_t)blockIdx.x;
+  const int64_t tile_step = (int64_t)gridDim.x;
+  const int64_t n_iters = (n_tiles > tile0) ? (n_tiles - tile0 + tile_step - 1) / tile_step : 0;
+
+  if (warp == kV2ConsumerWarps) {
+    // ================= producer: one thread streams CTA tiles into the ring =================
+    if (lane == 0) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(w) + tile0 * STAGE_BYTES;
+      const int64_t src_stride = (int64_t)gridDim.x * STAGE_BYTES;
+      int64_t left = n_elems * (int64_t)sizeof(InT) - tile0 * STAGE_BYTES;          // bytes from this tile to the end
+      uint32_t stage = 0, ph = 1;                                   // first pass over the ring: slots are free
+      for (int64_t it = 0; it < n_iters; ++it) {
+        mbar_wait(empty0 + 8 * stage, ph);
+        const uint32_t bytes = (left < STAGE_BYTES) ? (uint32_t)left : (uint32_t)STAGE_BYTES;
+        mbar_expect_tx(full0 + 8 * stage, bytes);
+        bulk_g2s(smem_u32(smem) + stage * STAGE_BYTES, src, bytes, full0 + 8 * stage);
+        src += src_stride;
+        left -= src_stride;
+        if (++stage == STAGES) { stage = 0; ph ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ================================ consumers =================================================
+  // per-thread invariants.  Output addresses are (thread base) + it * (byte stride): one IMAD.WIDE
+  // per store, no loop-carried 64-bit pointers.
+  const int64_t warp_e_first = tile0 * kV2CtaTile + (int64_t)warp * kV2WarpTile;
+  const int64_t e_first = warp_e_first + (int64_t)lane * 32;
+  const int64_t e_stride = tile_step * kV2CtaTile;
+  const uint32_t iters = (uint32_t)n_iters;
+  // iterations in which this thread's 32 elements exist (whole groups are valid or not)
+  const uint32_t valid_iters = (n_elems > e_first) ? (uint32_t)((n_elems - e_first + e_stride - 1) / e_stride) : 0u;
+  const uint32_t smem_thr = smem_u32(smem) + (uint32_t)warp * (kV2WarpTile * (uint32_t)sizeof(InT)) +
+                            (uint32_t)lane * (32u * (uint32_t)sizeof(InT));
+  Cons cons;
+  cons.init(lane, out.zq_log2, smem_u32(smem) + STAGES * STAGE_BYTES + (uint32_t)warp * (kV2WarpTile * 4));
+  uint32_t ld_off[NLD];
+#pragma unroll
+  for (int c = 0; c < NLD; ++c) {
+    ld_off[c] = smem_thr + (uint32_t)((F32IN ? (c ^ (lane & 7)) : ((c + cons.rot) & 3)) << 4);
+    asm volatile("" : "+r"(ld_off[c]));             // (no per-tile re-derivation from SR_CgaCtaId)
+  }
+  uint8_t* const q_base = reinterpret_cast<uint8_t*>(out.q_packed) + e_first * BITS / 8;
+  uint8_t* const s_base = reinterpret_cast<uint8_t*>(out.scales + e_first / G);
+  uint8_t* const z_base = reinterpret_cast<uint8_t*>(out.zp + e_first / G);
+  uint8_t* const zq_base = reinterpret_cast<uint8_t*>(out.zp_packed + ((e_first / G) >> out.zq_log2));
+  uint8_t* const qu_base = UNPACKED ? reinterpret_cast<uint8_t*>(out.q_unpacked + warp_e_first + 4 * lane) : nullptr;
+  const uint32_t q_step = (uint32_t)(e_stride * BITS / 8);         // bytes per iteration (< 2^32: grid <= 3*SMs)
+  const uint32_t s_step = (uint32_t)(e_stride / G) * 2u;
+  const uint32_t z_step = (uint32_t)(e_stride / G) * 4u;
+  const uint32_t zq_step = (uint32_t)((e_stride / G) >> out.zq_log2) * 4u;
+  const uint32_t qu_step = (uint32_t)e_stride * 4u;              // bytes per iteration (host keeps it < 2^32)
+  const bool has_zp = out.zp != nullptr, has_zq = out.zp_packed != nullptr, has_qp = out.q_packed != nullptr;
+
+  uint32_t stage = 0, ph = 0;
+  for (uint32_t it = 0; it < iters; ++it) {
+    const bool valid = it < valid_iters;
+    mbar_wait(full0 + 8 * stage, ph);
+    // 64 B per thread as 4 x LDS.128.  Register slot c holds 16-byte chunk (c + rot) & 3 of the
+    // thread's span: rotating the chunk order by lane/2 makes every quarter-warp hit 8 distinct
+    // bank groups.  Min/max and the per-word quantization are order independent; only the final
+    // 16-byte store has to rotate the 4 result words back (8 SELs).
+    uint32_t wds[4 * NLD];
+#pragma unroll
+    for (int c = 0; c < NLD; ++c) {
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(wds[4 * c]), "=r"(wds[4 * c + 1]), "=r"(wds[4 * c + 2]), "=r"(wds[4 * c + 3])
+                   : "r"(ld_off[c] + stage * STAGE_BYTES));
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * stage);   // slot is free as soon as it sits in registers
+    if (++stage == STAGES) { stage = 0; ph ^= 1u; }
+    // (threads past the end of the tensor compute on stale shared memory and store nothing)
+    cons.tile(wds, 0u, valid, q_base + (uint64_t)it * q_step, s_base + (uint64_t)it * s_step, z_base + (uint64_t)it * z_step,
+              zq_base + (uint64_t)it * zq_step, UNPACKED ? qu_base + (uint64_t)it * qu_step : nullptr,
+              UNPACKED ? n_elems - (warp_e_first + (int64_t)it * e_stride) : 0, has_qp, has_zp, has_zq);
   }
 }
 
-template <typename InT, int A, int G, bool UNPACKED, bool CS, int BITS>
-static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, V2ColScale csp, cudaStream_t st) {
-  int dev = 0, sms = 0;
-  AWQK_CUDA(cudaGetDevice(&dev));
-  AWQK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t want = (int64_t)sms * ((UNPACKED || sizeof(InT) == 4) ? 2 : 3);   // resident CTAs per SM (smem / register bound)
-  int64_t n_tiles;
-  unsigned grid;
-  if (CS) {
-    n_tiles = ceil_div(csp.C, kV2ConsumerWarps);                     // row blocks of a slab
-    csp.n_slabs = (int)(csp.K / kV2WarpTile);
-    int64_t cps = want / csp.n_slabs;
-    if (cps < 1) cps = 1;
-    if (cps > n_tiles) cps = n_tiles;
-    if (cps > 512) cps = 512;
-    csp.cps = (int)cps;
-    grid = (unsigned)(csp.n_slabs * cps);
-  } else {
-    n_tiles = ceil_div(n, kV2CtaTile);
-    grid = (unsigned)(n_tiles < want ? n_tiles : want);
+// ============================================================================================================
+// CS ("column scaled", the final AWQ pass: quantize fp32(w) * s[k], awqk.h col_scale), one launch for a BATCH of
+// tensors.  Every tensor [C, K] (K % 1024 == 0) is cut into column slabs of 1024 (one warp tile wide) and row chunks
+// of R rows; a UNIT is one row chunk of one slab, streamed 8 rows per stage (8 bulk copies of 2 KiB, one per consumer
+// warp), so that a thread's 32 columns -- and their scales -- stay the same for the whole unit.  Units are numbered
+// (tensor, row chunk, slab) with the slab fastest and dealt round-robin to the persistent CTAs: the CTAs that run at
+// the same time sweep the same rows of neighbouring slabs, which keeps the HBM pages of a row open.  The producer
+// warp also brings in the unit's 1024 column scales: all 32 lanes load them (8 x 16 B each, prefetched one unit
+// ahead) and store them transposed -- [chunk][lane] -- into one of two 4 KiB tables, handed over with a pair of
+// mbarriers per table.  Output offsets are (unit base) + tile * (constant stride) in the flat row-major arrays,
+// exactly as in the flat mode.
+// ============================================================================================================
+constexpr int kV2MaxBatch = 32;      // items of a launch (a tensor is one item, or two when its rows are split)
+constexpr int kV2MaxTensors = 31;
+struct V2BatchItem {
+  const void* w;
+  const float* s;       // [K]
+  uint32_t* q_packed;   // nullable when q_unpacked is given
+  int32_t* q_unpacked;  // nullable (UNPACKED instantiations only)
+  __half* scales;
+  int32_t* zp;          // nullable
+  uint32_t* zp_packed;  // nullable
+  int32_t C, K;
+  uint32_t unit_begin, unit_end;   // this item's units: [unit_begin, unit_end)
+  uint32_t n_slabs;                // K / 1024
+  uint32_t magic;                  // floor(2^32 / n_slabs) + 1 (n_slabs > 1): unit / n_slabs = umulhi(unit, magic)
+  uint32_t rows_per_unit;          // R, a multiple of 8 (tall units first, short ones for the tail of the launch)
+  uint32_t pad_;
+};
+struct V2Batch {
+  V2BatchItem it[kV2MaxBatch];
+  uint32_t n_units;
+  uint32_t has_zp, has_zq, has_qp;   // the same for every item of a launch
+};
+
+struct V2Unit {
+  uint32_t slab, row0, rows;         // rows: the unit's height (R, or what is left of the item)
+};
+__device__ __forceinline__ V2Unit v2_locate(const V2Batch& b, uint32_t u, uint32_t& t) {
+  while (u >= b.it[t].unit_end) ++t;                 // units are visited in increasing order
+  const uint32_t local = u - b.it[t].unit_begin;
+  const uint32_t ns = b.it[t].n_slabs;
+  const uint32_t R = b.it[t].rows_per_unit;
+  const uint32_t rc = (ns == 1) ? local : __umulhi(local, b.it[t].magic);
+  const uint32_t row0 = rc * R;
+  const uint32_t left = (uint32_t)b.it[t].C - row0;
+  return V2Unit{local - rc * ns, row0, left < R ? left : R};
+}
+
+template <typename InT, int G, bool SYM, bool UNPACKED>
+__global__ void __launch_bounds__(kV2Threads, UNPACKED ? 2 : 3)
+group_quant_tma_cs(const __grid_constant__ V2Batch b) {
+  using Cons = V2Consumer<InT, AR_F32, G, SYM, UNPACKED, true, 4>;
+  static_assert(sizeof(InT) == 2, "column-slab mode: bf16 / fp16 weights");
+  constexpr int STAGES = kV2Stages;
+  constexpr uint32_t STAGE_BYTES = kV2CtaTile * 2;
+  constexpr uint32_t ROW_BYTES = kV2WarpTile * 2;          // one warp tile = one row of the slab
+  constexpr uint32_t TABLE_BYTES = kV2WarpTile * 4;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t table0 = smem_u32(smem) + STAGES * STAGE_BYTES + (UNPACKED ? kV2UnpStageBytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (UNPACKED ? kV2UnpStageBytes : 0) + 2 * TABLE_BYTES);
+  uint32_t full0 = smem_u32(bars);
+  uint32_t empty0 = smem_u32(bars + STAGES);
+  uint32_t tfull0 = smem_u32(bars + 2 * STAGES);
+  uint32_t tempty0 = smem_u32(bars + 2 * STAGES + 2);
+  asm volatile("" : "+r"(full0), "+r"(empty0), "+r"(tfull0), "+r"(tempty0));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, kV2ConsumerWarps);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull0 + 8 * s, 1);
+      mbar_init(tempty0 + 8 * s, kV2ConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+
+  uint32_t u = blockIdx.x;
+  if (u >= b.n_units) return;
+
+  if (warp == kV2ConsumerWarps) {
+    // ================= producer warp: scale tables (all lanes) + W stages (lane 0) =================
+    const int rot0 = (lane >> 1) & 3;
+    float4 tab[8];
+    // lane l: its 32 scales of the slab, in the rotated chunk order of the W loads (slot c <- chunk (c + rot) & 3)
+    auto load_table = [&](const float* s, uint32_t slab) {
+      const float* sp0 = s + (size_t)slab * kV2WarpTile + lane * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) tab[2 * c + h] = __ldg(reinterpret_cast<const float4*>(sp0 + 8 * ((c + rot0) & 3) + 4 * h));
+      }
+    };
+    auto store_table = [&](uint32_t slot) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(table0 + slot * TABLE_BYTES + (uint32_t)j * 512u + (uint32_t)lane * 16u),
+                     "f"(tab[j].x), "f"(tab[j].y), "f"(tab[j].z), "f"(tab[j].w)
+                     : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tfull0 + 8 * slot);
+    };
+    uint32_t t = 0, tn = 0;                      // item cursors of the current / the next unit
+    V2Unit cur = v2_locate(b, u, t);
+    load_table(b.it[t].s, cur.slab);
+    store_table(0);
+    uint32_t stage = 0, ph = 1;                  // first pass over the ring: slots are free
+    for (uint32_t i = 0;; ++i) {
+      const uint32_t un = u + gridDim.x;
+      const bool has_next = un < b.n_units;
+      V2Unit nxt{0, 0, 0};
+      if (has_next) {
+        tn = t;
+        nxt = v2_locate(b, un, tn);
+        load_table(b.it[tn].s, nxt.slab);        // in flight while lane 0 issues this unit's stages
+      }
+      if (lane == 0) {
+        const int64_t row_bytes = (int64_t)b.it[t].K * 2;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(b.it[t].w) + (int64_t)cur.row0 * row_bytes + (int64_t)cur.slab * ROW_BYTES;
+        for (int rows_left = (int)cur.rows; rows_left > 0; rows_left -= kV2ConsumerWarps) {
+          mbar_wait(empty0 + 8 * stage, ph);
+          const int rows = rows_left < kV2ConsumerWarps ? rows_left : kV2ConsumerWarps;
+          mbar_expect_tx(full0 + 8 * stage, (uint32_t)rows * ROW_BYTES);
+          const uint32_t dst = smem_u32(smem) + stage * STAGE_BYTES;
+          for (int r = 0; r < rows; ++r) bulk_g2s(dst + r * ROW_BYTES, src + r * row_bytes, ROW_BYTES, full0 + 8 * stage);
+          src += kV2ConsumerWarps * row_bytes;
+          if (++stage == STAGES) { stage = 0; ph ^= 1u; }
+        }
+      }
+      __syncwarp();
+      if (!has_next) break;
+      const uint32_t slot = (i + 1) & 1u;
+      mbar_wait(tempty0 + 8 * slot, (((i + 1) >> 1) & 1u) ^ 1u);   // the consumers are done with this table's previous unit
+      store_table(slot);
+      u = un;
+      t = tn;
+      cur = nxt;
+    }
+    return;
+  }
+
+  // ================================ consumers =================================================
+  const uint32_t smem_thr = smem_u32(smem) + (uint32_t)warp * ROW_BYTES + (uint32_t)lane * 64u;
+  Cons cons;
+  cons.init(lane, 3, smem_u32(smem) + STAGES * STAGE_BYTES + (uint32_t)warp * (kV2WarpTile * 4));
+  uint32_t ld_off[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    ld_off[c] = smem_thr + (uint32_t)(((c + cons.rot) & 3) << 4);
+    asm volatile("" : "+r"(ld_off[c]));
+  }
+  const uint32_t cs_lane = table0 + (uint32_t)lane * 16u;
+
+  const bool has_zp = b.has_zp != 0, has_zq = b.has_zq != 0, has_qp = b.has_qp != 0;
+  uint32_t t = 0, stage = 0, ph = 0;
+  for (uint32_t i = 0; u < b.n_units; u += gridDim.x, ++i) {
+    const V2Unit un = v2_locate(b, u, t);
+    const V2BatchItem& item = b.it[t];
+    const int64_t K = item.K;
+    const int row = (int)un.row0 + warp;                        // this warp's row in the unit's first tile
+    int rows_left = (int)un.rows - warp;                        // > 0 <=> this warp's row of the current tile exists
+    const int64_t warp_e_first = (int64_t)row * K + (int64_t)un.slab * kV2WarpTile;
+    const int64_t e_first = warp_e_first + (int64_t)lane * 32;
+    uint8_t* q_dst = reinterpret_cast<uint8_t*>(item.q_packed) + e_first / 2;
+    uint8_t* s_dst = reinterpret_cast<uint8_t*>(item.scales + e_first / G);
+    uint8_t* z_dst = reinterpret_cast<uint8_t*>(item.zp + e_first / G);
+    uint8_t* zq_dst = reinterpret_cast<uint8_t*>(item.zp_packed + ((e_first / G) >> 3));
+    uint8_t* qu_dst = UNPACKED ? reinterpret_cast<uint8_t*>(item.q_unpacked + warp_e_first + 4 * lane) : nullptr;
+    // per tile (8 rows): q += 4K bytes, scales += 16 K/G, zp += 32 K/G, zp_packed += 4 K/G, int32 codes += 32K
+    uint32_t kq = (uint32_t)K * 4u, kg = (uint32_t)(K / G) * 4u;
+    asm volatile("" : "+r"(kq), "+r"(kg));                      // two live registers, no re-derivation from the item
+    const uint32_t slot = i & 1u;
+    const uint32_t cs_thr = cs_lane + slot * TABLE_BYTES;
+    mbar_wait(tfull0 + 8 * slot, (i >> 1) & 1u);
+    for (int tiles = ((int)un.rows + kV2ConsumerWarps - 1) / kV2ConsumerWarps; tiles > 0; --tiles) {
+      const bool valid = rows_left > 0;
+      mbar_wait(full0 + 8 * stage, ph);
+      uint32_t wds[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(wds[4 * c]), "=r"(wds[4 * c + 1]), "=r"(wds[4 * c + 2]), "=r"(wds[4 * c + 3])
+                     : "r"(ld_off[c] + stage * STAGE_BYTES));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty0 + 8 * stage);   // slot is free as soon as it sits in registers
+      if (++stage == STAGES) { stage = 0; ph ^= 1u; }
+      // (warps past the last row compute on stale shared memory and store nothing)
+      cons.tile(wds, cs_thr, valid, q_dst, s_dst, z_dst, zq_dst, qu_dst, valid ? (int64_t)kV2WarpTile : 0, has_qp, has_zp, has_zq);
+      q_dst += kq;
+      s_dst += kg * 4u;
+      z_dst += kg * 8u;
+      zq_dst += kg;
+      if (UNPACKED) qu_dst += (size_t)kq * 8u;
+      rows_left -= kV2ConsumerWarps;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty0 + 8 * slot);     // this warp no longer reads the table
+  }
+}
+
+static int v2_sms(int* sms) {
+  int dev = 0;
+  AWQK_CUDA(cudaGetDevice(&dev));
+  AWQK_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  return dev;
+}
+
+template <typename InT, int A, int G, bool UNPACKED, int BITS>
+static int launch_v2_sym(const InT* w, int64_t n, bool sym, V2Out out, cudaStream_t st) {
+  int sms = 0;
+  const int dev = v2_sms(&sms);
+  if (dev < 0) return dev;
+  const int64_t want = (int64_t)sms * ((UNPACKED || sizeof(InT) == 4) ? 2 : 3);   // resident CTAs per SM (smem / register bound)
+  const int64_t n_tiles = ceil_div(n, kV2CtaTile);
+  const unsigned grid = (unsigned)(n_tiles < want ? n_tiles : want);
   constexpr bool F32IN = sizeof(InT) == 4;                         // (same constants as in the kernel)
   constexpr int STAGES = F32IN ? (UNPACKED ? 2 : 3) : kV2Stages;
-  const size_t smem = (size_t)STAGES * kV2CtaTile * sizeof(InT) + (UNPACKED ? kV2UnpStageBytes : 0) +
-                      (CS ? kV2WarpTile * 4 : 0) + 2 * STAGES * sizeof(uint64_t);
+  const size_t smem = (size_t)STAGES * kV2CtaTile * sizeof(InT) + (UNPACKED ? kV2UnpStageBytes : 0) + 2 * STAGES * sizeof(uint64_t);
   // the dynamic-smem opt-in is per (kernel instantiation, device): set once, then immutable
   static std::atomic<uint64_t> configured[2] = {{0}, {0}};
   const uint64_t bit = 1ull << (dev & 63);
   const bool need = !(configured[sym ? 1 : 0].load(std::memory_order_acquire) & bit);
   if (sym) {
-    auto k = group_quant_tma<InT, A, G, true, UNPACKED, CS, BITS>;
+    auto k = group_quant_tma<InT, A, G, true, UNPACKED, BITS>;
     if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out, csp);
+    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
   } else {
-    auto k = group_quant_tma<InT, A, G, false, UNPACKED, CS, BITS>;
+    auto k = group_quant_tma<InT, A, G, false, UNPACKED, BITS>;
     if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out, csp);
+    k<<<grid, kV2Threads, smem, st>>>(w, n, n_tiles, out);
   }
   if (need) configured[sym ? 1 : 0].fetch_or(bit, std::memory_order_release);
   AWQK_CUDA(cudaGetLastError());
   return AWQK_OK;
 }
 
-template <typename InT, int A, bool CS, int BITS>
-static int launch_v2_g(const InT* w, int64_t n, int g, bool sym, V2Out out, V2ColScale csp, cudaStream_t st) {
+template <typename InT, int A, int BITS>
+static int launch_v2_g(const InT* w, int64_t n, int g, bool sym, V2Out out, cudaStream_t st) {
   if (out.q_unpacked != nullptr) {
     switch (g) {
-      case 32: return launch_v2_sym<InT, A, 32, true, CS, BITS>(w, n, sym, out, csp, st);
-      case 64: return launch_v2_sym<InT, A, 64, true, CS, BITS>(w, n, sym, out, csp, st);
-      default: return launch_v2_sym<InT, A, 128, true, CS, BITS>(w, n, sym, out, csp, st);
+      case 32: return launch_v2_sym<InT, A, 32, true, BITS>(w, n, sym, out, st);
+      case 64: return launch_v2_sym<InT, A, 64, true, BITS>(w, n, sym, out, st);
+      default: return launch_v2_sym<InT, A, 128, true, BITS>(w, n, sym, out, st);
     }
   }
   switch (g) {
-    case 32: return launch_v2_sym<InT, A, 32, false, CS, BITS>(w, n, sym, out, csp, st);
-    case 64: return launch_v2_sym<InT, A, 64, false, CS, BITS>(w, n, sym, out, csp, st);
-    default: return launch_v2_sym<InT, A, 128, false, CS, BITS>(w, n, sym, out, csp, st);
+    case 32: return launch_v2_sym<InT, A, 32, false, BITS>(w, n, sym, out, st);
+    case 64: return launch_v2_sym<InT, A, 64, false, BITS>(w, n, sym, out, st);
+    default: return launch_v2_sym<InT, A, 128, false, BITS>(w, n, sym, out, st);
   }
 }
 
 template <typename InT, int A>
 static int launch_v2_bits(const InT* w, int64_t n, int g, int bits, bool sym, V2Out out, cudaStream_t st) {
-  const V2ColScale none{nullptr, 0, 0, 0, 0};
-  return bits == 8 ? launch_v2_g<InT, A, false, 8>(w, n, g, sym, out, none, st)
-                   : launch_v2_g<InT, A, false, 4>(w, n, g, sym, out, none, st);
+  return bits == 8 ? launch_v2_g<InT, A, 8>(w, n, g, sym, out, st) : launch_v2_g<InT, A, 4>(w, n, g, sym, out, st);
 }
 
 // Entry used by awqk_group_quant: int4 / int8, bf16/fp16 input, flat layout (K % g == 0, g in {32,64,128},
@@ -699,30 +894,155 @@ int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, int
     return arith == AWQK_ARITH_FP32 ? launch_v2_bits<__nv_bfloat16, AR_F32>(p, n_elems, g, bits, sym, out, st)
                                     : launch_v2_bits<__nv_bfloat16, AR_BF16>(p, n_elems, g, bits, sym, out, st);
   }
-  if (dtype == AWQK_FP32) {           // int4 only (the dispatcher keeps 8-bit fp32 input on the register path)
-    const V2ColScale none{nullptr, 0, 0, 0, 0};
-    return launch_v2_g<float, AR_F32, false, 4>(reinterpret_cast<const float*>(w), n_elems, g, sym, out, none, st);
-  }
+  if (dtype == AWQK_FP32)             // int4 only (the dispatcher keeps 8-bit fp32 input on the register path)
+    return launch_v2_g<float, AR_F32, 4>(reinterpret_cast<const float*>(w), n_elems, g, sym, out, st);
   auto p = reinterpret_cast<const __half*>(w);
   return arith == AWQK_ARITH_FP32 ? launch_v2_bits<__half, AR_F32>(p, n_elems, g, bits, sym, out, st)
                                   : launch_v2_bits<__half, AR_F16>(p, n_elems, g, bits, sym, out, st);
 }
 
-// Column-scaled entry (col_scale != nullptr, fp32 arithmetic): needs K % 1024 == 0 and the per-iteration
-// output strides below 2^32 bytes; anything else stays on the register path.
+// ---- column-slab batches -----------------------------------------------------------------------------------
+// K % 1024 == 0, and the per-tile output strides (8 rows) below 2^32 bytes; anything else stays on the register path.
 bool group_quant_tma_cs_eligible(int64_t C, int64_t K) {
-  // largest per-iteration stride: cps (<= 512) * 8 rows * K elements * 4 bytes (int32 codes) < 2^32
-  return C > 0 && K % kV2WarpTile == 0 && K <= ((int64_t)1 << 32) / (8 * 4 * 512);
+  return C > 0 && C < ((int64_t)1 << 31) && K > 0 && K % kV2WarpTile == 0 && K <= ((int64_t)1 << 21);
+}
+
+template <typename InT, int G, bool UNPACKED>
+static int launch_cs_sym(const V2Batch& b, unsigned grid, bool sym, int dev, cudaStream_t st) {
+  const size_t smem = (size_t)kV2Stages * kV2CtaTile * 2 + (UNPACKED ? kV2UnpStageBytes : 0) + 2 * kV2WarpTile * 4 +
+                      (2 * kV2Stages + 4) * sizeof(uint64_t);
+  static std::atomic<uint64_t> configured[2] = {{0}, {0}};
+  const uint64_t bit = 1ull << (dev & 63);
+  const bool need = !(configured[sym ? 1 : 0].load(std::memory_order_acquire) & bit);
+  if (sym) {
+    auto k = group_quant_tma_cs<InT, G, true, UNPACKED>;
+    if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kV2Threads, smem, st>>>(b);
+  } else {
+    auto k = group_quant_tma_cs<InT, G, false, UNPACKED>;
+    if (need) AWQK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kV2Threads, smem, st>>>(b);
+  }
+  if (need) configured[sym ? 1 : 0].fetch_or(bit, std::memory_order_release);
+  AWQK_CUDA(cudaGetLastError());
+  return AWQK_OK;
+}
+
+template <typename InT, bool UNPACKED>
+static int launch_cs_g(const V2Batch& b, unsigned grid, int g, bool sym, int dev, cudaStream_t st) {
+  switch (g) {
+    case 32: return launch_cs_sym<InT, 32, UNPACKED>(b, grid, sym, dev, st);
+    case 64: return launch_cs_sym<InT, 64, UNPACKED>(b, grid, sym, dev, st);
+    default: return launch_cs_sym<InT, 128, UNPACKED>(b, grid, sym, dev, st);
+  }
+}
+
+// One launch over up to kV2MaxTensors eligible tensors (same dtype / group size / symmetry, and the same set of
+// outputs).  Units are dealt round-robin, so the launch takes (units per CTA) x (unit height): tall units keep the
+// hand-over cost (new table, new output bases: ~2 rows' worth) small, short units keep the last round short.  The
+// plan therefore uses units of r_main rows for as many whole rounds over the persistent grid as there are, and
+// units of r_tail rows for the rows that are left (the end of the tensor list); both heights are chosen per launch
+// by the cost model  rounds_main * (r_main + 2) + rounds_tail * (r_tail + 2).
+struct CsPlan {
+  V2Batch b;
+  int64_t cost;
+};
+
+// r_tail == 0: one height for everything
+static bool cs_plan(const awqk_quant_item* items, int n, int g, int64_t want, int r_main, int r_tail, CsPlan* plan) {
+  V2Batch& b = plan->b;
+  memset(&b, 0, sizeof(b));
+  int64_t units_main_all = 0;
+  for (int i = 0; i < n; ++i) units_main_all += (items[i].K / kV2WarpTile) * ceil_div(items[i].C, r_main);
+  const int64_t main_target = r_tail ? (units_main_all / want) * want : units_main_all;
+  if (r_tail && main_target == 0) return false;                 // less than one round: single-height plans cover it
+  int n_it = 0;
+  int64_t u = 0, units_main = 0;
+  bool tail = false;
+  for (int i = 0; i < n; ++i) {
+    const awqk_quant_item& s = items[i];
+    const int64_t slabs = s.K / kV2WarpTile;
+    int64_t split = s.C;                                        // rows [0, split) in tall units, [split, C) in short ones
+    if (tail) {
+      split = 0;
+    } else if (r_tail) {
+      const int64_t chunks = ceil_div(s.C, r_main);
+      if (units_main + slabs * chunks > main_target) {
+        split = ((main_target - units_main) / slabs) * r_main;
+        tail = true;
+      }
+    }
+    for (int part = 0; part < 2; ++part) {
+      const int64_t r0 = part ? split : 0, r1 = part ? s.C : split;
+      if (r1 <= r0) continue;
+      if (n_it == kV2MaxBatch) return false;
+      const int r = part ? r_tail : r_main;
+      const int64_t G = s.K / g;
+      V2BatchItem& d = b.it[n_it++];
+      d.w = reinterpret_cast<const uint8_t*>(s.w) + r0 * s.K * 2;
+      d.s = s.col_scale;
+      d.q_packed = s.q_packed ? s.q_packed + r0 * s.K / 8 : nullptr;
+      d.q_unpacked = s.q_unpacked ? s.q_unpacked + r0 * s.K : nullptr;
+      d.scales = reinterpret_cast<__half*>(s.scales_f16) + r0 * G;
+      d.zp = s.zp ? s.zp + r0 * G : nullptr;
+      d.zp_packed = s.zp_packed ? s.zp_packed + r0 * G / 8 : nullptr;
+      d.C = (int32_t)(r1 - r0);
+      d.K = (int32_t)s.K;
+      d.n_slabs = (uint32_t)slabs;
+      d.magic = slabs > 1 ? (uint32_t)(((uint64_t)1 << 32) / (uint64_t)slabs) + 1u : 0u;
+      d.rows_per_unit = (uint32_t)r;
+      d.unit_begin = (uint32_t)u;
+      const int64_t nu = slabs * ceil_div(r1 - r0, r);
+      u += nu;
+      if (!part) units_main += nu;
+      d.unit_end = (uint32_t)u;
+      if (u >= ((int64_t)1 << 31)) return false;
+    }
+  }
+  for (int i = n_it; i < kV2MaxBatch; ++i) b.it[i].unit_begin = b.it[i].unit_end = 0xFFFFFFFFu;   // sentinels: the item scan stops before
+  b.n_units = (uint32_t)u;
+  const int64_t units_tail = u - units_main;
+  plan->cost = ceil_div(units_main, want) * (r_main + 2) + (r_tail ? ceil_div(units_tail, want) * (r_tail + 2) : 0);
+  return u > 0;
+}
+
+int launch_group_quant_tma_cs_batch(const awqk_quant_item* items, int n, int dtype, int g, bool sym, cudaStream_t st) {
+  if (n <= 0 || n > kV2MaxTensors) return AWQK_E_BADARG;
+  int sms = 0;
+  const int dev = v2_sms(&sms);
+  if (dev < 0) return dev;
+  const bool unpacked = items[0].q_unpacked != nullptr;
+  const bool has_zp = items[0].zp != nullptr, has_zq = items[0].zp_packed != nullptr, has_qp = items[0].q_packed != nullptr;
+  for (int i = 1; i < n; ++i)
+    if ((items[i].q_unpacked != nullptr) != unpacked || (items[i].zp != nullptr) != has_zp ||
+        (items[i].zp_packed != nullptr) != has_zq || (items[i].q_packed != nullptr) != has_qp)
+      return AWQK_E_BADARG;
+  const int64_t want = (int64_t)sms * (unpacked ? 2 : 3);
+  CsPlan best, cand;
+  bool have = false;
+  for (int r_main = 8; r_main <= 128; r_main *= 2) {
+    for (int r_tail = 0; r_tail < r_main; r_tail = r_tail ? r_tail * 2 : 8) {
+      if (!cs_plan(items, n, g, want, r_main, r_tail, &cand)) continue;
+      if (!have || cand.cost < best.cost || (cand.cost == best.cost && r_tail == 0)) {
+        best = cand;
+        have = true;
+      }
+    }
+  }
+  if (!have) return AWQK_E_BADARG;
+  V2Batch& b = best.b;
+  b.has_zp = has_zp; b.has_zq = has_zq; b.has_qp = has_qp;
+  const unsigned grid = (unsigned)((int64_t)b.n_units < want ? (int64_t)b.n_units : want);
+  if (dtype == AWQK_BF16)
+    return unpacked ? launch_cs_g<__nv_bfloat16, true>(b, grid, g, sym, dev, st) : launch_cs_g<__nv_bfloat16, false>(b, grid, g, sym, dev, st);
+  return unpacked ? launch_cs_g<__half, true>(b, grid, g, sym, dev, st) : launch_cs_g<__half, false>(b, grid, g, sym, dev, st);
 }
 
 int launch_group_quant_tma_cs(const void* w, int dtype, int64_t C, int64_t K, int g, bool sym, const float* col_scale,
                               uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                               cudaStream_t st) {
-  V2Out out{q_packed, q_unpacked, reinterpret_cast<__half*>(scales), zp, zp_packed, 3};
-  const V2ColScale csp{col_scale, K, C, 0, 0};
-  if (dtype == AWQK_BF16)
-    return launch_v2_g<__nv_bfloat16, AR_F32, true, 4>(reinterpret_cast<const __nv_bfloat16*>(w), C * K, g, sym, out, csp, st);
-  return launch_v2_g<__half, AR_F32, true, 4>(reinterpret_cast<const __half*>(w), C * K, g, sym, out, csp, st);
+  const awqk_quant_item item{w, C, K, col_scale, q_unpacked, q_packed, scales, zp, zp_packed};
+  return launch_group_quant_tma_cs_batch(&item, 1, dtype, g, sym, st);
 }
 
 }  // namespace awqk

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define AWQK_VERSION 200
+#define AWQK_VERSION 210
 
 #if defined(__GNUC__)
 #define AWQK_API __attribute__((visibility("default")))
@@ -86,6 +86,25 @@ AWQK_API int awqk_group_quant(const void* w, int dtype, int64_t C, int64_t K, in
                      int symmetric, int arith, int32_t* q_unpacked, uint32_t* q_packed,
                      void* scales_f16, int32_t* zp, uint32_t* zp_packed, const float* col_scale,
                      void* stream);
+
+/* K1 over a BATCH of tensors in as few launches as possible: the same results as awqk_group_quant(item, ...) for
+ * every item, on `stream`.  Items that qualify for the column-slab kernel (col_scale given, bf16 / fp16 weights,
+ * bits = 4, arith = FP32, K % 1024 == 0, 16-byte aligned q_packed) are quantized by ONE persistent launch per 32
+ * tensors -- the final AWQ pass of a whole wave of linears (awq.py:435-457 loops over the model tensor by tensor) --
+ * which is what lets small tensors (a 1024 x 4096 k_proj is 2 us of HBM time) run at the bandwidth of large ones.
+ * Anything else falls back to one awqk_group_quant call per item.  `items` is a HOST array, read before returning. */
+typedef struct awqk_quant_item {
+  const void* w;          /* [C, K] */
+  int64_t C, K;
+  const float* col_scale; /* nullable fp32 [K] */
+  int32_t* q_unpacked;    /* nullable */
+  uint32_t* q_packed;     /* nullable */
+  void* scales_f16;
+  int32_t* zp;            /* nullable */
+  uint32_t* zp_packed;    /* nullable */
+} awqk_quant_item;
+AWQK_API int awqk_group_quant_batch(const awqk_quant_item* items, int n_items, int dtype, int group_size, int bits,
+                           int symmetric, int arith, void* stream);
 
 /* which kernel awqk_group_quant would pick: 1 = flat fast path, 0 = generic path, <0 error */
 AWQK_API int awqk_group_quant_path(int dtype, int64_t C, int64_t K, int group_size, int bits, int arith,

@@ -118,3 +118,88 @@ def test_colscale_matches_register_path(native_lib, cuda_device, monkeypatch):
     assert torch.equal(a["tensor_q"][:, :1536], b["tensor_q"])
     assert torch.equal(a["scales"][:, :12], b["scales"])
     assert torch.equal(a["zero_points"][:, :12], b["zero_points"])
+
+
+def _batch_case(native_lib, N, dev, shapes, dt, g, sym, *, unpacked, guard=False):
+    """awqk_group_quant_batch over `shapes` vs the oracle, tensor by tensor"""
+    from tests.test_gpu_parity import _canaries_intact, _guarded
+    items, keep, wants = [], [], []
+    for i, (C, K) in enumerate(shapes):
+        G = K // g
+        w = datagen.weights((C, K), dt, datagen.seed_of("csb", i, C, K, dt))
+        s = _scales(K, 31 * i + K)
+        wants.append(O.pack_result(O.quantize_scaled(w, s, 4, g, sym)))
+        sizes = {"q": C * K * 4, "qp": C * K // 2, "s": C * G * 2, "z": C * G * 4, "zq": C * -(-G // 8) * 4}
+        bufs = {k: _guarded(v, dev) for k, v in sizes.items()}
+        wd, sd = w.to(dev), s.to(dev)
+        keep.append((wd, sd, bufs, sizes, (C, K, G)))
+        items.append((wd, C, K, sd, bufs["q"][1] if unpacked else None, bufs["qp"][1], bufs["s"][1], bufs["z"][1], bufs["zq"][1]))
+    N.group_quant_batch(items, N.dtype_code(keep[0][0].dtype), g, 4, sym, N.ARITH_FP32, None)
+    torch.cuda.synchronize()
+    for i, ((wd, sd, bufs, sizes, (C, K, G)), want) in enumerate(zip(keep, wants)):
+        what = f"item {i} {C}x{K}"
+        for k, (b, _) in bufs.items():
+            if k == "q" and not unpacked:
+                continue
+            assert _canaries_intact(b, sizes[k]), f"{what}/{k} canary"
+        if unpacked:
+            assert_same(bufs["q"][1].view(torch.int32).reshape(C, K).cpu(), want["tensor_q"], what + "/q")
+        assert_same(bufs["qp"][1].view(torch.int32).reshape(C, K // 8).cpu(), want["qweight"], what + "/qweight")
+        assert_same(bufs["s"][1].view(torch.float16).reshape(C, G).cpu(), want["scales"], what + "/scales")
+        assert_same(bufs["z"][1].view(torch.int32).reshape(C, G).cpu(), want["zero_points"], what + "/zp")
+        if G % 8 == 0:
+            assert_same(bufs["zq"][1].view(torch.int32).reshape(C, G // 8).cpu(), want["qzeros"], what + "/qzeros")
+
+
+@pytest.mark.parametrize("unpacked", [False, True])
+@pytest.mark.parametrize("dt,g,sym", [("bf16", 128, False), ("fp16", 64, True), ("bf16", 32, False)])
+def test_colscale_batch_bit_exact(native_lib, cuda_device, dt, g, sym, unpacked):
+    """one launch over tensors of different heights and widths: units of several tensors interleave on a CTA,
+    ragged last row chunks (C % 8 != 0, C < 8), single-slab and many-slab tensors, guarded outputs"""
+    from awq_quantizer import _native as N
+    shapes = [(300, 4096), (1, 1024), (77, 3072), (8, 1024), (1029, 2048), (13, 7168), (5, 1024)]
+    _batch_case(native_lib, N, cuda_device, shapes, dt, g, sym, unpacked=unpacked)
+
+
+def test_colscale_batch_many_units_per_cta(native_lib, cuda_device):
+    """enough rows that every persistent CTA walks through many units (table double buffering, both parities of
+    the table barriers, tensors changing in the middle of a CTA's sequence)"""
+    from awq_quantizer import _native as N
+    shapes = [(8 * 700 + 3, 1024), (4099, 2048), (2500, 1024), (3001, 3072)]
+    _batch_case(native_lib, N, cuda_device, shapes, "bf16", 128, False, unpacked=False)
+
+
+def test_colscale_batch_more_than_one_launch_and_fallbacks(native_lib, cuda_device):
+    """> 32 eligible tensors (two launches) mixed with tensors the slab kernel does not take (K % 1024 != 0:
+    register path inside the same call)"""
+    from awq_quantizer import _native as N
+    shapes = [(16 + i, 1024 * (1 + i % 3)) for i in range(37)] + [(40, 1536), (9, 512)]
+    _batch_case(native_lib, N, cuda_device, shapes, "bf16", 128, False, unpacked=False)
+
+
+def test_colscale_batch_equals_single_calls(native_lib, cuda_device):
+    """Llama-3-8B layer shapes (q, k, v, o, gate, up, down) in one launch == seven awqk_group_quant calls"""
+    from awq_quantizer import _native as N
+    dev = cuda_device
+    shapes = [(4096, 4096), (1024, 4096), (1024, 4096), (4096, 4096), (14336, 4096), (14336, 4096), (4096, 14336)]
+    g = 128
+    single, items, outs = [], [], []
+    for i, (C, K) in enumerate(shapes):
+        G = K // g
+        gen = torch.Generator(device=dev).manual_seed(1000 + i)
+        w = (torch.randn((C, K), generator=gen, device=dev) * 0.02).to(torch.bfloat16)
+        s = torch.exp(0.5 * torch.randn(K, generator=gen, device=dev)).float()
+        mk = lambda: {"qp": torch.full((C, K // 8), 77, dtype=torch.int32, device=dev), "s": torch.zeros((C, G), dtype=torch.float16, device=dev),
+                      "z": torch.full((C, G), 77, dtype=torch.int32, device=dev), "zq": torch.full((C, G // 8), 77, dtype=torch.int32, device=dev)}
+        a, b = mk(), mk()
+        N.check(native_lib.awqk_group_quant(w.data_ptr(), N.BF16, C, K, g, 4, 0, N.ARITH_FP32, None, a["qp"].data_ptr(),
+                                            a["s"].data_ptr(), a["z"].data_ptr(), a["zq"].data_ptr(), s.data_ptr(), None))
+        single.append(a)
+        outs.append(b)
+        items.append((w, C, K, s, None, b["qp"], b["s"], b["z"], b["zq"]))
+    N.group_quant_batch(items, N.BF16, g, 4, False, N.ARITH_FP32, None)
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(single, outs)):
+        for k in a:
+            assert torch.equal(a[k].view(torch.int32) if k != "s" else a[k].view(torch.int16),
+                               b[k].view(torch.int32) if k != "s" else b[k].view(torch.int16)), (i, k)
