@@ -174,13 +174,17 @@ def quantize_with_search(qz, tensor: torch.Tensor, activations: torch.Tensor, de
 
 class SearchPipeline:
     """Runs the search (+ final pass) for many linears on the current stream: one ``awqk_scale_search`` call per
-    tensor, no host synchronisation, no torch kernels in between.  The scale grid is cached per activation tensor
-    (q/k/v or gate/up share theirs); one workspace serves every call (they are ordered by the stream)."""
+    tensor (scores, argmin, winning scales), then ONE ``awqk_group_quant_batch`` call per ``finish()`` for the final
+    column-scaled K1 pass of every tensor submitted since the last one -- a wave of linears is quantized by one
+    persistent launch per 31 tensors instead of one launch per tensor.  No host synchronisation, no torch kernels
+    in between.  The scale grid is cached per activation tensor (q/k/v or gate/up share theirs); one workspace
+    serves every call (they are ordered by the stream)."""
 
     def __init__(self, dev: torch.device, *, bits: int, group_size: int, symmetric: bool, n_grid: int = 20):
         self.dev, self.bits, self.g, self.sym, self.n_grid = dev, bits, group_size, symmetric, n_grid
         self.grid_cache = {}
         self.pending = []
+        self.finals = {}          # dtype code -> [(w, C, K, s_best, tensor_q, qweight, scales, zero_points, qzeros)]
         self.workspace = None
 
     def _grid(self, x: torch.Tensor):
@@ -202,8 +206,18 @@ class SearchPipeline:
             self.workspace = torch.empty(pref, dtype=torch.uint8, device=self.dev)
         s_grid, xb, _ = self._grid(x)
         r = scale_search(w, xb, s_grid, bits=self.bits, group_size=self.g, symmetric=self.sym,
-                         workspace=self.workspace, outputs=outputs, select=select)
+                         workspace=self.workspace, outputs=None, select=select)
+        if outputs is not None and outputs.get("scales") is not None:
+            self.finals.setdefault(N.dtype_code(w.dtype), []).append(
+                (w, C, K, r["s_best"], outputs.get("tensor_q"), outputs.get("qweight"), outputs["scales"],
+                 outputs.get("zero_points"), outputs.get("qzeros")))
         self.pending.append((name, r))
+
+    def flush_finals(self) -> None:
+        """the final pass group_quant(fp32(W) * s_best) of everything submitted so far, on the current stream"""
+        finals, self.finals = self.finals, {}
+        for code, items in finals.items():
+            N.group_quant_batch(items, code, self.g, self.bits, self.sym, N.ARITH_FP32, N.stream_ptr(self.dev))
 
     def drop_grid(self, x: torch.Tensor) -> None:
         """forget the cached grid of one activation tensor (its last linear has been submitted)"""
@@ -212,6 +226,7 @@ class SearchPipeline:
     def finish(self, keep_grids: bool = False):
         """[(name, err_mean fp64 [n_grid] (device), best_idx (device int32 0-d), s_best (device fp32 [K]))] in
         submission order, without a host sync"""
+        self.flush_finals()
         out = [(name, r["err_mean"], r["best_idx"], r["s_best"]) for name, r in self.pending]
         self.pending = []
         if not keep_grids:

@@ -147,6 +147,17 @@ struct PairQuant<AR_F32, QMIN, BITS> {
     const uint32_t r3 = __vimin_s16x2_relu(__byte_perm(__float_as_uint(t[1].y), __float_as_uint(t[3].y), sel), 0x000F000Fu);
     return (r3 * 16u + r2) * 256u + (r1 * 16u + r0);
   }
+  // the same without the clamp (FastGroup::noclamp for every group of the warp): the low halves are the codes
+  __device__ __forceinline__ uint32_t pack8_noclamp(const float2 (&q)[4], uint32_t sel) const {
+    float2 t[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) t[p] = __fadd2_rn(__fadd2_rn(q[p], zp2), magic2);
+    const uint32_t r0 = __byte_perm(__float_as_uint(t[0].x), __float_as_uint(t[2].x), sel);
+    const uint32_t r1 = __byte_perm(__float_as_uint(t[0].y), __float_as_uint(t[2].y), sel);
+    const uint32_t r2 = __byte_perm(__float_as_uint(t[1].x), __float_as_uint(t[3].x), sel);
+    const uint32_t r3 = __byte_perm(__float_as_uint(t[1].y), __float_as_uint(t[3].y), sel);
+    return (r3 * 16u + r2) * 256u + (r1 * 16u + r0);
+  }
 };
 template <int QMIN>
 struct PairQuant<AR_BF16, QMIN, 4> {
@@ -168,6 +179,7 @@ struct PairQuant<AR_BF16, QMIN, 4> {
     const __nv_bfloat162 t = __hadd2(__hadd2(__floats2bfloat162_rn(lo, hi), zp2), magic2);
     return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), rebase, 0x000F000Fu);
   }
+  __device__ __forceinline__ uint32_t pack8_noclamp(const float2 (&q)[4], uint32_t s) const { return pack8(q, s); }
   __device__ __forceinline__ uint32_t pack8(const float2 (&q)[4], uint32_t) const {   // (see PairQuant<AR_F32>)
     const uint32_t r0 = pair(q[0].x, q[2].x), r1 = pair(q[0].y, q[2].y), r2 = pair(q[1].x, q[3].x), r3 = pair(q[1].y, q[3].y);
     return (r3 * 16u + r2) * 256u + (r1 * 16u + r0);
@@ -193,6 +205,7 @@ struct PairQuant<AR_F16, QMIN, 4> {
     const __half2 t = __hadd2(__hadd2(__floats2half2_rn(lo, hi), zp2), magic2);
     return __viaddmin_s16x2_relu(*reinterpret_cast<const uint32_t*>(&t), rebase, 0x000F000Fu);
   }
+  __device__ __forceinline__ uint32_t pack8_noclamp(const float2 (&q)[4], uint32_t s) const { return pack8(q, s); }
   __device__ __forceinline__ uint32_t pack8(const float2 (&q)[4], uint32_t) const {
     const uint32_t r0 = pair(q[0].x, q[2].x), r1 = pair(q[0].y, q[2].y), r2 = pair(q[1].x, q[3].x), r3 = pair(q[1].y, q[3].y);
     return (r3 * 16u + r2) * 256u + (r1 * 16u + r0);
@@ -205,6 +218,7 @@ struct PairQuant<AR_F16, QMIN, 4> {
 template <int QMIN>
 struct PairQuant<AR_BF16, QMIN, 8> {
   __device__ __forceinline__ uint32_t pack8(const float2 (&)[4], uint32_t) const { return 0u; }   // int4 only
+  __device__ __forceinline__ uint32_t pack8_noclamp(const float2 (&)[4], uint32_t) const { return 0u; }
   __nv_bfloat162 zp2;
   float2 magic2;
   __device__ __forceinline__ void prepare() { magic2 = make_float2(12582912.0f - (float)QMIN, 12582912.0f - (float)QMIN); }
@@ -220,6 +234,7 @@ struct PairQuant<AR_BF16, QMIN, 8> {
 template <int QMIN>
 struct PairQuant<AR_F16, QMIN, 8> {
   __device__ __forceinline__ uint32_t pack8(const float2 (&)[4], uint32_t) const { return 0u; }   // int4 only
+  __device__ __forceinline__ uint32_t pack8_noclamp(const float2 (&)[4], uint32_t) const { return 0u; }
   __half2 zp2;
   float2 magic2;
   __device__ __forceinline__ void prepare() { magic2 = make_float2(12582912.0f - (float)QMIN, 12582912.0f - (float)QMIN); }
@@ -274,7 +289,7 @@ struct V2Consumer {
   static constexpr float FQMIN = (float)QMIN, FQMAX = (float)(QMIN + (int)CMAX);
 
   int lane, rot, odd_shift, LPW;
-  uint32_t half_sel, zq_shift, zq_mask;
+  uint32_t half_sel, zq_shift, zq_mask, zq_lane_mask;
   bool leader, zq_writer;
   uint32_t stg_w[8], stg_r[8];
   PairQuant<A, QMIN, BITS> pq;
@@ -290,6 +305,7 @@ struct V2Consumer {
     odd_shift = (F32IN && (lane & 1)) ? 2 : 0;
     leader = (lane % LPG) == 0;
     zq_writer = (lane & (LPW - 1)) == 0;
+    zq_lane_mask = leader ? CMAX : 0u;
     zq_shift = (uint32_t)BITS * ((uint32_t)(lane / LPG) & ((1u << zq_log2) - 1u));
     zq_mask = (LPW == 32) ? 0xFFFFFFFFu : (((1u << LPW) - 1u) << (lane & ~(LPW - 1)));
     // UNPACKED: warp-private staging of 256 x 16 B chunks.  Thread l owns logical chunks 8l..8l+7 (4 codes
@@ -331,15 +347,26 @@ struct V2Consumer {
         for (int i = 0; i < 16; ++i)
           xv[i] = make_float2(__uint_as_float(wds[(2 * i) % (4 * NLD)]), __uint_as_float(wds[(2 * i + 1) % (4 * NLD)]));
       }
-      mn = fmin3_nan(xv[0].x, xv[0].y, xv[1].x);
-      mx = fmax3_nan(xv[0].x, xv[0].y, xv[1].x);
-      mn = v2_fmin_nan(mn, xv[1].y);
-      mx = v2_fmax_nan(mx, xv[1].y);
+      // 16 three-input operations per statistic, as four independent chains of depth 3 (one per LDS chunk of W:
+      // a chain starts as soon as its chunk is there) and a merge of depth 4 -- not one chain of depth 16
+      float pmn[4], pmx[4];
 #pragma unroll
-      for (int i = 2; i < 16; ++i) {
-        mn = fmin3_nan(mn, xv[i].x, xv[i].y);
-        mx = fmax3_nan(mx, xv[i].x, xv[i].y);
+      for (int c = 0; c < 4; ++c) {
+        pmn[c] = fmin3_nan(xv[4 * c].x, xv[4 * c].y, xv[4 * c + 1].x);
+        pmx[c] = fmax3_nan(xv[4 * c].x, xv[4 * c].y, xv[4 * c + 1].x);
+        pmn[c] = fmin3_nan(pmn[c], xv[4 * c + 1].y, xv[4 * c + 2].x);
+        pmx[c] = fmax3_nan(pmx[c], xv[4 * c + 1].y, xv[4 * c + 2].x);
+        pmn[c] = fmin3_nan(pmn[c], xv[4 * c + 2].y, xv[4 * c + 3].x);
+        pmx[c] = fmax3_nan(pmx[c], xv[4 * c + 2].y, xv[4 * c + 3].x);
       }
+      mn = fmin3_nan(pmn[0], pmn[1], pmn[2]);
+      mx = fmax3_nan(pmx[0], pmx[1], pmx[2]);
+      mn = fmin3_nan(mn, pmn[3], xv[3].y);
+      mx = fmax3_nan(mx, pmx[3], xv[3].y);
+      mn = fmin3_nan(mn, xv[7].y, xv[11].y);
+      mx = fmax3_nan(mx, xv[7].y, xv[11].y);
+      mn = v2_fmin_nan(mn, xv[15].y);
+      mx = v2_fmax_nan(mx, xv[15].y);
     } else {
       uint32_t mn2 = wds[0], mx2 = wds[0];
 #pragma unroll
@@ -370,14 +397,16 @@ struct V2Consumer {
     //   8 bit: every mode rounds through the fp32 magic -> 2^14
     constexpr float LIM = (A == AR_F32 || BITS == 8) ? 16384.0f : ((A == AR_BF16) ? 48.0f : 400.0f);
     const bool fast = fg.ok && (fmaxf(fabsf(mn), fabsf(mx)) < sc * LIM);
+    // asymmetric int4 in fp32 arithmetic: when no group of the warp needs the final clamp (the normal case: every
+    // group straddles zero) the 16 VIMNMX of the tile are skipped -- the ALU pipe is the busiest one of this kernel
+    constexpr bool NOCLAMP_OK = !SYM && A == AR_F32 && BITS == 4;
+    const bool noclamp = NOCLAMP_OK && __all_sync(0xFFFFFFFFu, fast && fg.noclamp);
     if (fast) {
       pq.init(fg.zp);
       zi = __float2int_rz(fg.zp);
       const float2 r2 = make_float2(fg.rcp, fg.rcp);
       const float2 ns2 = make_float2(-sc, -sc);
-#pragma unroll
-      for (int wi = 0; wi < 4; ++wi) {
-        float2 qv[4];
+      auto quotients = [&](int wi, float2 (&qv)[4]) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const float2 x = (CS || F32IN) ? xv[(CS || F32IN) ? 4 * wi + p : 0] : Packed<InT>::to_f2(wds[4 * wi + p]);
@@ -385,11 +414,25 @@ struct V2Consumer {
           const float2 e = __ffma2_rn(ns2, q0, x);
           qv[p] = __ffma2_rn(e, r2, q0);                          // correctly rounded x / s
         }
-        if (BITS == 4) {
-          words[wi * (NW / 4)] = pq.pack8(qv, half_sel);
-        } else {                                                  // int8: bytes 0 and 2 of each pair (u_lo | u_hi << 16)
-          words[wi * (NW / 4)] = __byte_perm(pq.run(qv[0]), pq.run(qv[1]), 0x6420);
-          words[wi * (NW / 4) + (NW / 4 - 1)] = __byte_perm(pq.run(qv[2]), pq.run(qv[3]), 0x6420);
+      };
+      if (NOCLAMP_OK && noclamp) {
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+          float2 qv[4];
+          quotients(wi, qv);
+          words[wi * (NW / 4)] = pq.pack8_noclamp(qv, half_sel);
+        }
+      } else {
+#pragma unroll
+        for (int wi = 0; wi < 4; ++wi) {
+          float2 qv[4];
+          quotients(wi, qv);
+          if (BITS == 4) {
+            words[wi * (NW / 4)] = pq.pack8(qv, half_sel);
+          } else {                                                // int8: bytes 0 and 2 of each pair (u_lo | u_hi << 16)
+            words[wi * (NW / 4)] = __byte_perm(pq.run(qv[0]), pq.run(qv[1]), 0x6420);
+            words[wi * (NW / 4) + (NW / 4 - 1)] = __byte_perm(pq.run(qv[2]), pq.run(qv[3]), 0x6420);
+          }
         }
       }
     } else {
@@ -490,7 +533,8 @@ struct V2Consumer {
       if (has_zp) *reinterpret_cast<int32_t*>(z_dst) = zi;
     }
     if (has_zq) {
-      const uint32_t uz = (valid && leader && zi != INT32_MIN) ? ((uint32_t)(zi - QMIN) & CMAX) : 0u;
+      // (a NaN zero point -- INT32_MIN, asymmetric only, QMIN = 0 -- packs as 0 by itself: its low bits are 0)
+      const uint32_t uz = valid ? ((uint32_t)(zi - QMIN) & zq_lane_mask) : 0u;
       // (a compile-time full mask lets the compiler drop the re-convergence sequence around REDUX: the common
       // g = 128 / int4 case packs one word per warp)
       const uint32_t wordz = (LPW == 32) ? __reduce_or_sync(0xFFFFFFFFu, uz << zq_shift)
@@ -784,22 +828,23 @@ group_quant_tma_cs(const __grid_constant__ V2Batch b) {
     const V2BatchItem& item = b.it[t];
     const int64_t K = item.K;
     const int row = (int)un.row0 + warp;                        // this warp's row in the unit's first tile
-    int rows_left = (int)un.rows - warp;                        // > 0 <=> this warp's row of the current tile exists
     const int64_t warp_e_first = (int64_t)row * K + (int64_t)un.slab * kV2WarpTile;
     const int64_t e_first = warp_e_first + (int64_t)lane * 32;
-    uint8_t* q_dst = reinterpret_cast<uint8_t*>(item.q_packed) + e_first / 2;
-    uint8_t* s_dst = reinterpret_cast<uint8_t*>(item.scales + e_first / G);
-    uint8_t* z_dst = reinterpret_cast<uint8_t*>(item.zp + e_first / G);
-    uint8_t* zq_dst = reinterpret_cast<uint8_t*>(item.zp_packed + ((e_first / G) >> 3));
-    uint8_t* qu_dst = UNPACKED ? reinterpret_cast<uint8_t*>(item.q_unpacked + warp_e_first + 4 * lane) : nullptr;
-    // per tile (8 rows): q += 4K bytes, scales += 16 K/G, zp += 32 K/G, zp_packed += 4 K/G, int32 codes += 32K
-    uint32_t kq = (uint32_t)K * 4u, kg = (uint32_t)(K / G) * 4u;
-    asm volatile("" : "+r"(kq), "+r"(kg));                      // two live registers, no re-derivation from the item
+    uint8_t* const q_base = reinterpret_cast<uint8_t*>(item.q_packed) + e_first / 2;
+    uint8_t* const s_base = reinterpret_cast<uint8_t*>(item.scales + e_first / G);
+    uint8_t* const z_base = reinterpret_cast<uint8_t*>(item.zp + e_first / G);
+    uint8_t* const zq_base = reinterpret_cast<uint8_t*>(item.zp_packed + ((e_first / G) >> 3));
+    uint8_t* const qu_base = UNPACKED ? reinterpret_cast<uint8_t*>(item.q_unpacked + warp_e_first + 4 * lane) : nullptr;
+    // tile j (8 rows further down): q + j * 4K bytes, scales + j * 16 K/G, zp + j * 32 K/G, zp_packed + j * 4 K/G,
+    // int32 codes + j * 32K -- one IMAD.WIDE per store
+    const uint32_t kq = (uint32_t)K * 4u, kg = (uint32_t)(K / G) * 4u;
     const uint32_t slot = i & 1u;
     const uint32_t cs_thr = cs_lane + slot * TABLE_BYTES;
+    const uint32_t n_tiles = (un.rows + kV2ConsumerWarps - 1) / kV2ConsumerWarps;
+    // tiles in which this warp's row exists (the warps past the last row of a ragged unit only keep the ring going)
+    const uint32_t my_tiles = ((int)un.rows > warp) ? (un.rows - (uint32_t)warp + kV2ConsumerWarps - 1) / kV2ConsumerWarps : 0u;
     mbar_wait(tfull0 + 8 * slot, (i >> 1) & 1u);
-    for (int tiles = ((int)un.rows + kV2ConsumerWarps - 1) / kV2ConsumerWarps; tiles > 0; --tiles) {
-      const bool valid = rows_left > 0;
+    for (uint32_t j = 0; j < n_tiles; ++j) {
       mbar_wait(full0 + 8 * stage, ph);
       uint32_t wds[16];
 #pragma unroll
@@ -811,14 +856,10 @@ group_quant_tma_cs(const __grid_constant__ V2Batch b) {
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * stage);   // slot is free as soon as it sits in registers
       if (++stage == STAGES) { stage = 0; ph ^= 1u; }
-      // (warps past the last row compute on stale shared memory and store nothing)
-      cons.tile(wds, cs_thr, valid, q_dst, s_dst, z_dst, zq_dst, qu_dst, valid ? (int64_t)kV2WarpTile : 0, has_qp, has_zp, has_zq);
-      q_dst += kq;
-      s_dst += kg * 4u;
-      z_dst += kg * 8u;
-      zq_dst += kg;
-      if (UNPACKED) qu_dst += (size_t)kq * 8u;
-      rows_left -= kV2ConsumerWarps;
+      if (j < my_tiles)                                 // (warp-uniform)
+        cons.tile(wds, cs_thr, true, q_base + (uint64_t)j * kq, s_base + (uint64_t)j * (kg * 4u), z_base + (uint64_t)j * (kg * 8u),
+                  zq_base + (uint64_t)j * kg, UNPACKED ? qu_base + (uint64_t)j * kq * 8u : nullptr, (int64_t)kV2WarpTile,
+                  has_qp, has_zp, has_zq);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(tempty0 + 8 * slot);     // this warp no longer reads the table

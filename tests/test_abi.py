@@ -43,7 +43,7 @@ def test_library_is_sm100a_only(native_lib):
 
 
 def test_version_and_error_strings(native_lib):
-    assert native_lib.awqk_version() == 200
+    assert native_lib.awqk_version() == 210
     assert native_lib.awqk_error_string(0) == b"ok"
     assert b"argument" in native_lib.awqk_error_string(-1)
     assert native_lib.awqk_error_string(-99) == b"unknown error"
