@@ -28,6 +28,8 @@ SIGNATURES = {
                                 _vp, _vp]),
     "awqk_group_quant_path": (_int, [_int, _i64, _i64, _int, _int, _int, _vp]),
     "awqk_group_quant_batch": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp]),
+    "awqk_group_quant_batch_plan": (_int, [C.POINTER(_i64), C.POINTER(_i64), _int, _int, _int, _int, C.POINTER(_i64),
+                                           C.POINTER(_i64), _int]),
     "awqk_dequant": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp, _vp]),
     "awqk_dequant_packed": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _int, _vp, _vp]),
     "awqk_bf16_to_fp16": (_int, [_vp, _vp, _i64, _vp]),

@@ -458,6 +458,8 @@ int launch_group_quant_tma_cs(const void* w, int dtype, int64_t C, int64_t K, in
                               uint32_t* q_packed, int32_t* q_unpacked, void* scales, int32_t* zp, uint32_t* zp_packed,
                               cudaStream_t st);
 int launch_group_quant_tma_cs_batch(const awqk_quant_item* items, int n, int dtype, int g, bool sym, cudaStream_t st);
+int cs_plan_describe(const int64_t* C, const int64_t* K, int n, int g, bool unpacked, int sms, int64_t* summary, int64_t* rows,
+                     int max_items);
 constexpr int kCsMaxBatch = 31;   // = kV2MaxTensors
 
 // does awqk_group_quant send this call to the column-slab kernel?
@@ -622,4 +624,11 @@ extern "C" int awqk_group_quant_batch(const awqk_quant_item* items, int n_items,
     if (rc != AWQK_OK) return rc;
   }
   return AWQK_OK;
+}
+
+extern "C" int awqk_group_quant_batch_plan(const int64_t* C, const int64_t* K, int n_tensors, int group_size, int with_int32_codes,
+                                           int sms, int64_t* summary5, int64_t* items4, int max_items) {
+  if (C == nullptr || K == nullptr || summary5 == nullptr || (max_items > 0 && items4 == nullptr)) return AWQK_E_BADARG;
+  if (!(group_size == 32 || group_size == 64 || group_size == 128)) return AWQK_E_BADARG;
+  return cs_plan_describe(C, K, n_tensors, group_size, with_int32_codes != 0, sms, summary5, items4, max_items);
 }

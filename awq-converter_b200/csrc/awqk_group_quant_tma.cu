@@ -987,11 +987,17 @@ static int launch_cs_g(const V2Batch& b, unsigned grid, int g, bool sym, int dev
 struct CsPlan {
   V2Batch b;
   int64_t cost;
+  int r_main, r_tail;
+  int n_items;
+  int tensor_of[kV2MaxBatch];       // launch item -> index into the caller's tensor list
+  int64_t row_begin[kV2MaxBatch];   // first row of the tensor the item covers
 };
 
 // r_tail == 0: one height for everything
 static bool cs_plan(const awqk_quant_item* items, int n, int g, int64_t want, int r_main, int r_tail, CsPlan* plan) {
   V2Batch& b = plan->b;
+  plan->r_main = r_main;
+  plan->r_tail = r_tail;
   memset(&b, 0, sizeof(b));
   int64_t units_main_all = 0;
   for (int i = 0; i < n; ++i) units_main_all += (items[i].K / kV2WarpTile) * ceil_div(items[i].C, r_main);
@@ -1019,6 +1025,8 @@ static bool cs_plan(const awqk_quant_item* items, int n, int g, int64_t want, in
       if (n_it == kV2MaxBatch) return false;
       const int r = part ? r_tail : r_main;
       const int64_t G = s.K / g;
+      plan->tensor_of[n_it] = i;
+      plan->row_begin[n_it] = r0;
       V2BatchItem& d = b.it[n_it++];
       d.w = reinterpret_cast<const uint8_t*>(s.w) + r0 * s.K * 2;
       d.s = s.col_scale;
@@ -1042,9 +1050,48 @@ static bool cs_plan(const awqk_quant_item* items, int n, int g, int64_t want, in
   }
   for (int i = n_it; i < kV2MaxBatch; ++i) b.it[i].unit_begin = b.it[i].unit_end = 0xFFFFFFFFu;   // sentinels: the item scan stops before
   b.n_units = (uint32_t)u;
+  plan->n_items = n_it;
   const int64_t units_tail = u - units_main;
   plan->cost = ceil_div(units_main, want) * (r_main + 2) + (r_tail ? ceil_div(units_tail, want) * (r_tail + 2) : 0);
   return u > 0;
+}
+
+static bool cs_best_plan(const awqk_quant_item* items, int n, int g, int64_t want, CsPlan* best) {
+  CsPlan cand;
+  bool have = false;
+  for (int r_main = 8; r_main <= 128; r_main *= 2) {
+    for (int r_tail = 0; r_tail < r_main; r_tail = r_tail ? r_tail * 2 : 8) {
+      if (!cs_plan(items, n, g, want, r_main, r_tail, &cand)) continue;
+      if (!have || cand.cost < best->cost || (cand.cost == best->cost && r_tail == 0)) {
+        *best = cand;
+        have = true;
+      }
+    }
+  }
+  return have;
+}
+
+// introspection for tests (awqk_group_quant_batch_plan): no device needed
+int cs_plan_describe(const int64_t* C, const int64_t* K, int n, int g, bool unpacked, int sms, int64_t* summary, int64_t* rows,
+                     int max_items) {
+  if (n <= 0 || n > kV2MaxTensors || sms <= 0) return AWQK_E_BADARG;
+  awqk_quant_item items[kV2MaxTensors];
+  memset(items, 0, sizeof(items));
+  for (int i = 0; i < n; ++i) {
+    if (!group_quant_tma_cs_eligible(C[i], K[i]) || K[i] % g != 0) return AWQK_E_UNSUPPORTED;
+    items[i].C = C[i];
+    items[i].K = K[i];
+  }
+  CsPlan best;
+  if (!cs_best_plan(items, n, g, (int64_t)sms * (unpacked ? 2 : 3), &best)) return AWQK_E_BADARG;
+  summary[0] = best.r_main; summary[1] = best.r_tail; summary[2] = best.b.n_units; summary[3] = best.n_items; summary[4] = best.cost;
+  for (int i = 0; i < best.n_items && i < max_items; ++i) {
+    rows[4 * i] = best.tensor_of[i];
+    rows[4 * i + 1] = best.row_begin[i];
+    rows[4 * i + 2] = best.b.it[i].C;
+    rows[4 * i + 3] = best.b.it[i].rows_per_unit;
+  }
+  return AWQK_OK;
 }
 
 int launch_group_quant_tma_cs_batch(const awqk_quant_item* items, int n, int dtype, int g, bool sym, cudaStream_t st) {
@@ -1059,18 +1106,8 @@ int launch_group_quant_tma_cs_batch(const awqk_quant_item* items, int n, int dty
         (items[i].zp_packed != nullptr) != has_zq || (items[i].q_packed != nullptr) != has_qp)
       return AWQK_E_BADARG;
   const int64_t want = (int64_t)sms * (unpacked ? 2 : 3);
-  CsPlan best, cand;
-  bool have = false;
-  for (int r_main = 8; r_main <= 128; r_main *= 2) {
-    for (int r_tail = 0; r_tail < r_main; r_tail = r_tail ? r_tail * 2 : 8) {
-      if (!cs_plan(items, n, g, want, r_main, r_tail, &cand)) continue;
-      if (!have || cand.cost < best.cost || (cand.cost == best.cost && r_tail == 0)) {
-        best = cand;
-        have = true;
-      }
-    }
-  }
-  if (!have) return AWQK_E_BADARG;
+  CsPlan best;
+  if (!cs_best_plan(items, n, g, want, &best)) return AWQK_E_BADARG;
   V2Batch& b = best.b;
   b.has_zp = has_zp; b.has_zq = has_zq; b.has_qp = has_qp;
   const unsigned grid = (unsigned)((int64_t)b.n_units < want ? (int64_t)b.n_units : want);

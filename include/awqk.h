@@ -106,6 +106,15 @@ typedef struct awqk_quant_item {
 AWQK_API int awqk_group_quant_batch(const awqk_quant_item* items, int n_items, int dtype, int group_size, int bits,
                            int symmetric, int arith, void* stream);
 
+/* Introspection (tests, tools; no device needed): the unit plan of ONE column-slab launch over tensors [C[i], K[i]]
+ * (n_tensors <= 31, all eligible) on a device with `sms` SMs.  A tensor is cut into column slabs of 1024 and row chunks;
+ * a unit = one row chunk of one slab; units are dealt round-robin to 3 (2 with int32 codes) persistent CTAs per SM.
+ *   summary5: tall unit height, short unit height (0 = none), units, launch items, modelled cost (rows per CTA)
+ *   items4  : per launch item (tensor index, first row, rows, unit height) -- the items partition every tensor's rows;
+ *             short units cover the END of the tensor list, so that the last round over the grid stays short. */
+AWQK_API int awqk_group_quant_batch_plan(const int64_t* C, const int64_t* K, int n_tensors, int group_size,
+                                int with_int32_codes, int sms, int64_t* summary5, int64_t* items4, int max_items);
+
 /* which kernel awqk_group_quant would pick: 1 = flat fast path, 0 = generic path, <0 error */
 AWQK_API int awqk_group_quant_path(int dtype, int64_t C, int64_t K, int group_size, int bits, int arith,
                           const void* w);

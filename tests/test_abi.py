@@ -83,3 +83,64 @@ def test_host_copy_without_gpu(native_lib):
     _native.host_copy(d, c)
     assert torch.equal(c, d)
     assert native_lib.awqk_host_copy(None, None, 16, 2) == -1
+
+
+def _plan(native_lib, shapes, g=128, unpacked=0, sms=148):
+    n = len(shapes)
+    C = (ctypes.c_int64 * n)(*[s[0] for s in shapes])
+    K = (ctypes.c_int64 * n)(*[s[1] for s in shapes])
+    summ = (ctypes.c_int64 * 5)()
+    items = (ctypes.c_int64 * (4 * 32))()
+    rc = native_lib.awqk_group_quant_batch_plan(C, K, n, g, unpacked, sms, summ, items, 32)
+    return rc, list(summ), [tuple(items[4 * i:4 * i + 4]) for i in range(int(summ[3]))] if rc == 0 else []
+
+
+def test_batch_plan_partitions_every_tensor(native_lib):
+    """the unit plan of the column-slab launch (awqk_group_quant_batch): the launch items partition the rows of
+    every tensor in order, short units only at the end of the tensor list, unit count consistent, and the modelled
+    cost never above the best single-height plan"""
+    import random
+    rnd = random.Random(7)
+    layer = [(4096, 4096), (1024, 4096), (1024, 4096), (4096, 4096), (14336, 4096), (14336, 4096), (4096, 14336)]
+    cases = [[(8192, 28672)], [(28672, 8192)], [(1, 1024)], [(7, 2048), (9, 1024)], layer, layer * 4, [(4096, 4096)] * 31]
+    for _ in range(40):
+        cases.append([(rnd.randint(1, 20000), 1024 * rnd.randint(1, 28)) for _ in range(rnd.randint(1, 31))])
+    for shapes in cases:
+        for unpacked in (0, 1):
+            rc, (r_main, r_tail, units, n_items, cost), items = _plan(native_lib, shapes, unpacked=unpacked)
+            assert rc == 0, (rc, shapes)
+            grid = 148 * (2 if unpacked else 3)
+            assert r_main in (8, 16, 32, 64, 128) and r_tail in (0, 8, 16, 32, 64) and r_tail < r_main
+            assert 1 <= n_items <= 32 and len(items) == n_items
+            # partition: per tensor, consecutive row ranges starting at 0 and ending at C, in tensor order
+            pos = {}
+            order = []
+            seen_short = False
+            u = 0
+            for t, r0, rows, r in items:
+                assert r in (r_main, r_tail) and r > 0 and rows > 0
+                assert r0 == pos.get(t, 0), (shapes, items)
+                pos[t] = r0 + rows
+                order.append(t)
+                if r != r_main:
+                    seen_short = True
+                else:
+                    assert not seen_short, "tall units after the short tail"
+                u += (shapes[t][1] // 1024) * -(-rows // r)
+            assert order == sorted(order)
+            assert all(pos.get(t, 0) == c for t, (c, _) in enumerate(shapes)), (shapes, items)
+            assert u == units
+            # never worse than the best single-height plan under the same cost model
+            single = min(-(-sum((k // 1024) * -(-c // r) for c, k in shapes) // grid) * (r + 2) for r in (8, 16, 32, 64, 128))
+            assert cost <= single, (cost, single, shapes)
+            # and close to the ideal (total rows x slabs / grid) for launches of at least a few rounds
+            ideal = sum(c * (k // 1024) for c, k in shapes) / grid
+            if ideal >= 256:
+                assert cost <= 1.06 * ideal + 12, (cost, ideal, shapes)
+
+
+def test_batch_plan_rejects_bad_arguments(native_lib):
+    assert _plan(native_lib, [(16, 1536)])[0] == -4            # K % 1024 != 0: not a column-slab tensor
+    assert _plan(native_lib, [(16, 1024)] * 32)[0] == -1       # more than 31 tensors per launch
+    assert _plan(native_lib, [(16, 1024)], sms=0)[0] == -1
+    assert _plan(native_lib, [(16, 1024)], g=48)[0] == -1
