@@ -104,6 +104,9 @@ __device__ __forceinline__ void delta16(const float2 (&wv)[8], const float2 (&sv
     mx = dq_fmax_nan(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
   }
   const FastGroup fg = group_params_fast<AR_F32, BITS>(mn, mx, sym, qmin, qmax);
+  // asymmetric groups that straddle zero cannot produce a code outside [qmin, qmax] (FastGroup::noclamp): when that
+  // holds for every group of the warp -- the normal case -- the four FMNMX per pair of the clamp are skipped
+  const bool noclamp = __all_sync(0xFFFFFFFFu, fg.ok && fg.noclamp);
   if (fg.ok) {
     const float2 r2 = make_float2(fg.rcp, fg.rcp), ns2 = make_float2(-fg.scale, -fg.scale);
     // rint(v) - zp = (v + M) - (M + zp): M + zp is an exact integer below 2^24, the difference of two such
@@ -111,13 +114,7 @@ __device__ __forceinline__ void delta16(const float2 (&wv)[8], const float2 (&sv
     const float2 zp2 = make_float2(fg.zp, fg.zp);
     const float2 nmz2 = make_float2(-(12582912.0f + fg.zp), -(12582912.0f + fg.zp));
     const float2 sc2 = make_float2(fg.scale, fg.scale);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 q0 = __fmul2_rn(x[i], r2);
-      const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x[i]), r2, q0);              // x / scale, exact
-      float2 v = __fadd2_rn(q, zp2);
-      v.x = fminf(fmaxf(v.x, qmin), qmax);                                         // clamp commutes with rint
-      v.y = fminf(fmaxf(v.y, qmin), qmax);
+    auto finish = [&](int i, float2 v) {
       const float2 d = __fmul2_rn(__fadd2_rn(__fadd2_rn(v, magic2), nmz2), sc2);   // (rint(v) - zp) * scale
       const float2 ri = rs(i);
       const float2 h0 = __fmul2_rn(d, ri);
@@ -126,6 +123,24 @@ __device__ __forceinline__ void delta16(const float2 (&wv)[8], const float2 (&sv
       const float2 dl = __fadd2_rn(wv[i], make_float2(-what.x, -what.y));          // W - W^
       const __nv_bfloat162 b = __float22bfloat162_rn(dl);
       o[i] = *reinterpret_cast<const uint32_t*>(&b);
+    };
+    if (noclamp) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 q0 = __fmul2_rn(x[i], r2);
+        const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x[i]), r2, q0);            // x / scale, exact
+        finish(i, __fadd2_rn(q, zp2));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 q0 = __fmul2_rn(x[i], r2);
+        const float2 q = __ffma2_rn(__ffma2_rn(ns2, q0, x[i]), r2, q0);            // x / scale, exact
+        float2 v = __fadd2_rn(q, zp2);
+        v.x = fminf(fmaxf(v.x, qmin), qmax);                                       // clamp commutes with rint
+        v.y = fminf(fmaxf(v.y, qmin), qmax);
+        finish(i, v);
+      }
     }
   } else {                                                         // non-finite / constant / extreme groups
     const GroupParams gp = group_params<AR_F32>(mn, mx, sym, qmin, qmax);

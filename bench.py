@@ -77,7 +77,8 @@ def measured_peaks():
         with open(path) as f:
             d = json.load(f)
         sus = float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)))
-        return {"hbm": float(d["hbm_gbs"]), "tf_sustained": sus, "tf_burst": float(d.get("bf16_tflops_burst", sus)),
+        return {"hbm": float(d["hbm_gbs"]), "tf_sustained": sus,
+                "tf_burst": float(d.get("bf16_tflops_burst", d.get("bf16_tflops", sus))),
                 "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm": 6650.0, "tf_sustained": 1590.0, "tf_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
@@ -510,9 +511,12 @@ def run_native(args):
         pack_launch = f"direct launches (graph capture failed: {str(e)[:80]})"
         torch.cuda.synchronize(dev)
     # burst: the pass alone at the clocks a kernel timed in isolation gets.  The legs above leave the GPU in its
-    # power-capped state (~1.3 GHz); K1 is issue-bound enough to feel that, so the clocks get ~0.1 s of this same
-    # pass to recover first.  The sustained figure below is the pass back to back until the power cap bites again.
+    # power-capped state (~1.3 GHz, a moving power average); K1 in column-slab mode is bound by the SM's FMA / issue
+    # rate, i.e. by the clock, so the GPU idles 1.5 s and then gets ~0.1 s of this same pass to ramp up first.  The
+    # sustained figure below is the pass back to back for >= 1.2 s, until the power cap bites again (~1.75 GHz).
     burst, burst_mine = [], []
+    barrier()
+    time.sleep(1.5)                                # let the power-cap window of the tensor-core legs run out
     timed(pack_pass, 1, 24)
     for _ in range(5):
         ms, mine_ms = timed(pack_pass, 4, 0)
