@@ -2,7 +2,7 @@
 on the B200 path:
 
 * every flag of main.py:32-157 is accepted unchanged; additive flags: ``--pack`` (int32-packed
-  qweight/qzeros next to or instead of the unpacked codes), ``--arith {native,fp32}``, ``--config``
+  qweight/qzeros next to the unpacked codes; ``--packed_only``: instead of them), ``--arith {native,fp32}``, ``--config``
   (the YAML file the reference documents but never wired, main.py:16 / USAGE.md:13-22),
   ``--calibration_file`` / ``--n_grid`` (activation-aware alpha search for the weights it names);
 * tensor selection = main.py:243-253 (non-float / empty / numel < 128 are skipped, largest first);
@@ -62,6 +62,9 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--chunk_size", type=int, default=10, help="Number of tensors to save in each chunk (for large models)")
     # additive
     p.add_argument("--pack", action="store_true", help="emit int32-packed qweight/qzeros (8 nibbles per word)")
+    p.add_argument("--packed_only", action="store_true",
+                   help="with --pack: leave out the unpacked int32 codes (the reference's `tensor_q` / `.q`, 4 bytes "
+                        "per weight: 8x the packed size on the PCIe link and on disk)")
     p.add_argument("--arith", type=str, default="native", choices=["native", "fp32"],
                    help="arithmetic contract: native = the reference's own (input dtype), fp32 = reference on w.float()")
     p.add_argument("--config", type=str, help="YAML config (reference schema); CLI flags win over it")
@@ -343,7 +346,8 @@ def _rank_work(args, logger, rank: int, world: int, local: int) -> dict:
             # compatibility and not needed.
             acts = {n: calib[n] for n, t in shard.items() if n in calib and t.dim() == 2}
             try:
-                return qz.quantize_model(shard, activations=acts or None, pack=args.pack, keep_unpacked=True)
+                return qz.quantize_model(shard, activations=acts or None, pack=args.pack,
+                                         keep_unpacked=not (args.pack and args.packed_only))
             except Exception as e:
                 logger.error(f"Error processing shard on {device}: {e}")
                 return {}

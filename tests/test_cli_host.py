@@ -29,6 +29,7 @@ def test_cli_flags_and_defaults_match_reference():
     assert (a.num_workers, a.max_memory, a.multi_gpu, a.batch_size, a.prefetch_factor, a.chunk_size) == \
         (4, 0.8, False, 10, 2, 10)
     assert a.save_safetensors is False and a.log_level == "INFO" and a.pack is False and a.arith == "native"
+    assert a.packed_only is False
     helptext = subprocess.run([sys.executable, "-c",
                                "import sys; sys.path.insert(0, %r); from awq_quantizer.main import parse_args; "
                                "parse_args(['--help'])" % os.path.join(ROOT, "awq-converter_b200")],

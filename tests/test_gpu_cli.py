@@ -89,6 +89,19 @@ def test_cli_calibration_file_runs_search(native_lib, cuda_device, tmp_path):
     assert int(r["best_idx"]) == int(want["best_idx"]) and torch.equal(r["qweight"], want["qweight"])
     assert torch.equal(r["awq_scale"], want["awq_scale"])
     assert "awq_scale" not in got["layers.0.fc2.weight"]
+    # --packed_only: the same packed results without the int32 codes (searched and plain tensors alike)
+    out2 = str(tmp_path / "out_awq_packed")
+    rc = cli.main(["--model_id", model, "--output_dir", out2, "--device", "cuda:0", "--calibration_file", calib,
+                   "--n_grid", "8", "--pack", "--packed_only", "--log_level", "ERROR", "--chunk_size", "100"])
+    assert rc == 0
+    got2 = torch.load(os.path.join(out2, "model_chunk_0000.pt"))
+    assert set(got2) == set(got)
+    for name, r2 in got2.items():
+        assert "tensor_q" not in r2 and "tensor_q" in got[name]
+        for k in ("qweight", "qzeros", "scales"):
+            assert torch.equal(r2[k], got[name][k]), (name, k)
+        if "zero_points" in r2:                    # (kept by the search path: small; the packed form is qzeros)
+            assert torch.equal(r2["zero_points"], got[name]["zero_points"]), name
 
 
 def test_cli_passthrough_of_unquantized_tensors(native_lib, cuda_device, tmp_path):

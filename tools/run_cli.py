@@ -17,17 +17,23 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="opt-350m")
 ap.add_argument("--pack", action="store_true")
 ap.add_argument("--save_safetensors", action="store_true")
+ap.add_argument("--packed_only", action="store_true")
 ap.add_argument("--keep", action="store_true")
+ap.add_argument("--search", action="store_true", help="write a calibration file (T tokens per searched linear) and pass --calibration_file")
+ap.add_argument("--tokens", type=int, default=2048)
+ap.add_argument("--runs", type=int, default=2)
 args = ap.parse_args()
 
 work = tempfile.mkdtemp(prefix="awq_cli_")
 src, dst = os.path.join(work, "model"), os.path.join(work, "out")
 os.makedirs(src)
-gen = torch.Generator().manual_seed(7)
+gdev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")      # synthetic data is generated where it is fast
+gen = torch.Generator(device=gdev).manual_seed(7)
 specs = M.workload(args.workload)
 shard, nbytes, fi, total = {}, 0, 0, 0
+t_gen = time.perf_counter()
 for name, shape, _ in specs:
-    shard[name] = (torch.randn(shape, generator=gen, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+    shard[name] = (torch.randn(shape, generator=gen, device=gdev, dtype=torch.float32) * 0.02).to(torch.bfloat16).cpu()
     nbytes += shard[name].numel() * 2
     if nbytes > (2 << 30):
         save_file(shard, os.path.join(src, f"model-{fi:05d}.safetensors")); fi += 1; total += nbytes; shard, nbytes = {}, 0
@@ -35,12 +41,31 @@ if shard:
     save_file(shard, os.path.join(src, f"model-{fi:05d}.safetensors")); total += nbytes
 del shard
 argv = ["--model_id", src, "--output_dir", dst, "--log_level", "ERROR", "--chunk_size", "64"]
+calib_bytes = 0
+if args.search:                                   # {weight name: activations [T, K]} -- the CLI's calibration format
+    acts, cache = {}, {}
+    for name, shape, ck in specs:
+        if ck is None or len(shape) != 2:
+            continue
+        key = (ck, shape[1])
+        if key not in cache:
+            gain = torch.exp(torch.randn(shape[1], generator=gen, device=gdev))
+            cache[key] = (torch.randn((args.tokens, shape[1]), generator=gen, device=gdev) * gain).to(torch.bfloat16).cpu()
+        acts[name] = cache[key].clone()                 # (safetensors refuses tensors that share storage)
+    calib_path = os.path.join(work, "calibration.safetensors")
+    save_file(acts, calib_path)
+    calib_bytes = os.path.getsize(calib_path)
+    del acts, cache
+    argv += ["--calibration_file", calib_path]
+t_gen = time.perf_counter() - t_gen
 if args.pack:
     argv.append("--pack")
 if args.save_safetensors:
     argv.append("--save_safetensors")
+if args.packed_only:
+    argv.append("--packed_only")
 runs = []
-for it in range(2):
+for it in range(args.runs):
     shutil.rmtree(dst, ignore_errors=True)
     t0 = time.perf_counter()
     rc = cli.main(argv)
@@ -49,7 +74,9 @@ for it in range(2):
 meta = json.load(open(os.path.join(dst, "metadata.json")))
 out_bytes = sum(os.path.getsize(os.path.join(dst, f)) for f in os.listdir(dst))
 print(json.dumps({"workload": args.workload, "cli": "awq_quantizer " + " ".join(argv[4:]), "bf16_GB": total / 1e9,
-                  "tensors_quantized": meta["num_tensors"], "wall_s_first_run": round(runs[0], 3), "wall_s_second_run": round(runs[1], 3),
+                  "calibration_GB": calib_bytes / 1e9, "synthetic_checkpoint_written_in_s": round(t_gen, 1),
+                  "tensors_quantized": meta["num_tensors"], "wall_s_first_run": round(runs[0], 3),
+                  "wall_s_second_run": round(runs[-1], 3) if len(runs) > 1 else None,
                   "output_GB": out_bytes / 1e9, "note": "load_tensors + quantize + save chunks, one process, 1 GPU"}))
 if not args.keep:
     shutil.rmtree(work, ignore_errors=True)
