@@ -232,3 +232,33 @@ def test_cli_two_ranks_fail_together_without_hanging(tmp_path):
     assert "no CPU execution path" in (r.stderr + r.stdout)
     assert not os.path.exists(tmp_path / "out" / "metadata.json") or \
         json.load(open(tmp_path / "out" / "metadata.json"))["num_tensors"] == 0
+
+
+def test_native_safetensors_writer_round_trip(tmp_path):
+    """write_safetensors (straight from the tensors' memory, no serialisation buffer) produces files the stock
+    safetensors reader accepts, for every dtype / rank the result dicts hold, views of larger arrays included"""
+    from safetensors.torch import load_file
+    from safetensors import safe_open
+    big = torch.arange(4096, dtype=torch.int32)
+    flat = {"a.q": big[128:128 + 64].view(4, 16), "a.scales": torch.randn(4, 2).to(torch.float16),
+            "a.zero_points": torch.arange(8, dtype=torch.int32).view(4, 2), "a.bits": torch.tensor(4, dtype=torch.int32).reshape(1),
+            "a.symmetric": torch.tensor(True).reshape(1), "b.w": torch.randn(3, 5).to(torch.bfloat16),
+            "b.f": torch.randn(7), "b.d": torch.randn(2, 2, dtype=torch.float64), "b.i64": torch.arange(3),
+            "b.u8": torch.arange(5, dtype=torch.uint8), "b.i8": torch.arange(-2, 3, dtype=torch.int8),
+            "b.empty": torch.empty((0, 4), dtype=torch.float16), "b.t": torch.arange(12, dtype=torch.int32).view(3, 4).t()}
+    path = str(tmp_path / "x.safetensors")
+    cli.write_safetensors(flat, path)
+    back = load_file(path)
+    assert sorted(back) == sorted(flat)
+    for k, v in flat.items():
+        assert back[k].dtype == v.dtype and back[k].shape == v.shape and torch.equal(back[k], v), k
+    with safe_open(path, framework="pt") as f:                 # header is well formed for slicing readers too
+        assert f.get_slice("a.q").get_shape() == [4, 16]
+    with pytest.raises(ValueError):
+        cli.write_safetensors({"c": torch.zeros(2, dtype=torch.complex64)}, str(tmp_path / "y.safetensors"))
+    # many chunks -> several writer threads
+    q = {f"t{i}": fake_qdict((4, 256), pack=True) for i in range(23)}
+    meta = cli.save_model_in_chunks(q, str(tmp_path / "many"), chunk_size=2, use_safetensors=True)
+    assert meta["num_chunks"] == 12 and meta["files"] == [f"model_chunk_{c:04d}.safetensors" for c in range(12)]
+    got = load_file(str(tmp_path / "many" / "model_chunk_0011.safetensors"))
+    assert torch.equal(got["t22.qweight"], q["t22"]["qweight"])

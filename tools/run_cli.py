@@ -77,6 +77,6 @@ print(json.dumps({"workload": args.workload, "cli": "awq_quantizer " + " ".join(
                   "calibration_GB": calib_bytes / 1e9, "synthetic_checkpoint_written_in_s": round(t_gen, 1),
                   "tensors_quantized": meta["num_tensors"], "wall_s_first_run": round(runs[0], 3),
                   "wall_s_second_run": round(runs[-1], 3) if len(runs) > 1 else None,
-                  "output_GB": out_bytes / 1e9, "note": "load_tensors + quantize + save chunks, one process, 1 GPU"}))
+                  "output_GB": out_bytes / 1e9, "timing_s_last_run": meta.get("timing_s_rank0"), "note": "load_tensors + quantize + save chunks, one process, 1 GPU"}))
 if not args.keep:
     shutil.rmtree(work, ignore_errors=True)
