@@ -49,6 +49,8 @@ SIGNATURES = {
     "awqk_pipe_quant_gather": (_int, [_vp, _int, C.POINTER(_vp), C.POINTER(_i64), _i64, _int, _int, _int, _int, _int,
                                       _vp, _vp, _vp, _vp, _vp]),
     "awqk_host_copy": (_int, [_vp, _vp, C.c_size_t, _int]),
+    "awqk_host_alloc_pinned": (_int, [C.c_size_t, C.POINTER(_vp)]),
+    "awqk_host_free_pinned": (_int, [_vp]),
     "awqk_pipe_sync": (_int, [_vp]),
 }
 
@@ -138,3 +140,51 @@ def group_quant_batch(items, dtype_code_: int, group_size: int, bits: int, symme
         a.q_unpacked, a.q_packed, a.scales_f16, a.zp, a.zp_packed = ptr(qu), ptr(qp), sc.data_ptr(), ptr(zp), ptr(zq)
     check(lib().awqk_group_quant_batch(C.cast(arr, _vp), len(items), dtype_code_, group_size, bits, int(symmetric), arith,
                                        stream), "awqk_group_quant_batch")
+
+
+# ---- page-locked staging buffers (awqk_host_alloc_pinned) with a small process-wide cache -------------------------
+# torch.empty(pin_memory=True) is cudaHostAlloc: ~0.1 s per 256 MB on these hosts.  The native allocator page-locks a
+# pre-faulted huge-page mapping in place (~15 ms per 256 MB).  Buffers are handed out as uint8 tensors and come back to
+# the cache when their user is done; the cache keeps at most _PIN_CACHE_BYTES and frees the oldest blocks beyond that.
+_PIN_CACHE_BYTES = 3 << 30
+_pin_lock = threading.Lock()
+_pin_free = []            # [(nbytes, ptr, tensor)] oldest first
+_pin_live = {}            # ptr -> nbytes of blocks currently handed out
+
+
+def pinned_take(nbytes: int):
+    """a page-locked uint8 tensor of exactly ``nbytes`` (from the cache when one of that size is free)"""
+    import torch
+    nbytes = max(int(nbytes), 256)
+    with _pin_lock:
+        for i, (nb, ptr, t) in enumerate(_pin_free):
+            if nb == nbytes:
+                _pin_free.pop(i)
+                _pin_live[ptr] = nb
+                return t
+    out = _vp()
+    check(lib().awqk_host_alloc_pinned(nbytes, C.byref(out)), "awqk_host_alloc_pinned")
+    t = torch.frombuffer((C.c_ubyte * nbytes).from_address(out.value), dtype=torch.uint8)
+    with _pin_lock:
+        _pin_live[out.value] = nbytes
+    return t
+
+
+def pinned_give_back(t) -> None:
+    """return a tensor obtained from pinned_take (all copies that use it must have finished)"""
+    if t is None:
+        return
+    ptr = t.data_ptr()
+    drop = []
+    with _pin_lock:
+        nb = _pin_live.pop(ptr, None)
+        if nb is None:
+            return                                  # not one of ours (e.g. torch's own pinned allocation)
+        _pin_free.append((nb, ptr, t))
+        total = sum(b for b, _, _ in _pin_free)
+        while total > _PIN_CACHE_BYTES and len(_pin_free) > 1:
+            b, p, _t = _pin_free.pop(0)
+            total -= b
+            drop.append(p)
+    for p in drop:
+        lib().awqk_host_free_pinned(p)

@@ -90,6 +90,16 @@ class WaveUploader(threading.Thread):
         self._released[wi] = event
         self._released_flag[wi].set()
 
+    def give_back(self) -> None:
+        """after join(): the staging slots return to the process-wide cache (their H2D copies must have finished)"""
+        try:
+            self.stream.synchronize()
+        except Exception:
+            pass
+        for i, t in enumerate(self.h_slot):
+            self.h_slot[i] = None
+            N.pinned_give_back(t)
+
     def abort(self) -> None:
         self._abort.set()
 
@@ -110,7 +120,7 @@ class WaveUploader(threading.Thread):
                 if self.d_slot[slot] is None:
                     self.d_slot[slot] = torch.empty(self.slot_bytes, dtype=torch.uint8, device=self.dev)
                     if self.need_stage:
-                        self.h_slot[slot] = torch.empty(self.slot_bytes, dtype=torch.uint8, pin_memory=True)
+                        self.h_slot[slot] = N.pinned_take(self.slot_bytes)     # ~15 ms per 256 MB (cudaHostAlloc: ~100)
                 views, off = {}, 0
                 for n in wave:
                     t = self.tensors[n]
@@ -184,8 +194,9 @@ class ResultSink:
         self.stream = torch.cuda.Stream(dev)
         self.host: Dict[str, Dict[str, torch.Tensor]] = {}
         self._inflight = []                                       # pinned mode: (device tensors, D2H-done event)
-        self._ring = [] if pin_results else [torch.empty(max(slot_bytes, 256), dtype=torch.uint8, pin_memory=True)
-                                             for _ in range(min(3, n_waves))]
+        # ring slots are page-locked on first use (one by one, behind the first waves' compute), not up front
+        self._ring_bytes = max(slot_bytes, 256)
+        self._ring: List[Optional[torch.Tensor]] = [] if pin_results else [None] * min(3, n_waves)
         self._q: "queue.Queue" = queue.Queue()
         self._free = threading.Semaphore(max(1, len(self._ring)))
         self._err: list = []
@@ -233,6 +244,8 @@ class ResultSink:
         if self._err:
             raise self._err[0]
         slot = wi % len(self._ring)
+        if self._ring[slot] is None:
+            self._ring[slot] = N.pinned_take(self._ring_bytes)
         self.stream.wait_event(computed)
         with torch.cuda.stream(self.stream):
             self._ring[slot][:used].copy_(d_arena[:used], non_blocking=True)
@@ -251,6 +264,8 @@ class ResultSink:
             if self._err:
                 raise self._err[0]
             slot = wi % len(self._ring)
+            if self._ring[slot] is None:
+                self._ring[slot] = N.pinned_take(self._ring_bytes)
             entries, off = [], 0
             self.stream.wait_event(computed)
             with torch.cuda.stream(self.stream):
@@ -292,12 +307,23 @@ class ResultSink:
         if self._prefault is not None:
             self._prefault.join(timeout=60)
         if failed:
+            try:
+                self.stream.synchronize()               # nothing may still be writing into the ring
+                self._give_back_ring()
+            except Exception:
+                pass
             return
         if self._err:
             raise self._err[0]
         self.stream.synchronize()
         torch.cuda.current_stream(self.dev).wait_stream(self.stream)
         self._inflight.clear()
+        self._give_back_ring()
+
+    def _give_back_ring(self) -> None:
+        for i, t in enumerate(self._ring):
+            self._ring[i] = None
+            N.pinned_give_back(t)
 
 
 def plan_activation_buffers(waves: List[List[str]], activations: Dict[str, torch.Tensor], dev: torch.device,
@@ -459,6 +485,8 @@ def quantize_model_with_search(qz, tensors: Dict[str, torch.Tensor], activations
         raise
     finally:
         uploader.join(timeout=60)
+        if not uploader.is_alive():
+            uploader.give_back()
     out: Dict[str, Dict[str, torch.Tensor]] = {}
     for name in names:
         host = sink.host[name]

@@ -70,8 +70,8 @@ extern "C" void awqk_pipe_destroy(awqk_pipe* p) {
     if (p->ev_k[b]) (void)cudaEventDestroy(p->ev_k[b]);
     if (p->ev_out[b]) (void)cudaEventDestroy(p->ev_out[b]);
     if (p->ev_h2d[b]) (void)cudaEventDestroy(p->ev_h2d[b]);
-    if (p->h_in[b]) (void)cudaFreeHost(p->h_in[b]);
-    if (p->h_out[b]) (void)cudaFreeHost(p->h_out[b]);
+    if (p->h_in[b]) (void)awqk_host_free_pinned(p->h_in[b]);
+    if (p->h_out[b]) (void)awqk_host_free_pinned(p->h_out[b]);
   }
   if (p->s_in) (void)cudaStreamDestroy(p->s_in);
   if (p->s_k) (void)cudaStreamDestroy(p->s_k);
@@ -392,6 +392,72 @@ extern "C" int awqk_host_prefault(void* ptr, size_t bytes, int threads) {
   return AWQK_OK;
 }
 
+// Page-locked staging memory at memcpy speed: cudaHostAlloc takes ~0.1 s per 256 MB on these hosts (2.4 GB/s: it faults
+// and pins 4 KiB pages on one thread) -- three upload slots, three result slots and the gather rings were 0.4 s of a
+// 1.1 s first call.  Here: a 2 MiB-aligned anonymous mapping, transparent huge pages requested, every page touched by
+// the copy threads, then page-locked IN PLACE with cudaHostRegister (~15 ms per 256 MB; tools/probe_register.py).
+// The block starts with one header page (kind, mapping size) so that awqk_host_free_pinned needs no global table.
+namespace {
+constexpr size_t kPinAlign = (size_t)2 << 20;
+struct PinHeader {
+  uint64_t magic;
+  uint64_t map_bytes;
+  uint64_t registered;     // 1: mmap + cudaHostRegister, 0: cudaHostAlloc fallback (then map_bytes = 0)
+};
+constexpr uint64_t kPinMagic = 0x6177716b70696e31ull;   // "awqkpin1"
+}  // namespace
+
+extern "C" int awqk_host_alloc_pinned(size_t bytes, void** out) {
+  if (out == nullptr || bytes == 0) return AWQK_E_BADARG;
+  *out = nullptr;
+  const size_t body = (bytes + kPinAlign - 1) & ~(kPinAlign - 1);
+  const size_t total = body + 2 * kPinAlign;                  // slack to align the body, header in front of it
+  void* raw = mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (raw != MAP_FAILED) {
+    // body = the first 2 MiB boundary that leaves room for the header page in front of it
+    uint8_t* b = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 4096 + kPinAlign - 1) & ~(uintptr_t)(kPinAlign - 1));
+    // give back what lies in front of the header page and behind the body
+    uint8_t* head = b - 4096;
+    if (head > static_cast<uint8_t*>(raw)) (void)munmap(raw, (size_t)(head - static_cast<uint8_t*>(raw)));
+    uint8_t* end = b + body;
+    uint8_t* raw_end = static_cast<uint8_t*>(raw) + total;
+    if (raw_end > end) (void)munmap(end, (size_t)(raw_end - end));
+    (void)awqk_host_prefault(b, body, 0);
+    if (cudaHostRegister(b, body, cudaHostRegisterPortable) == cudaSuccess) {
+      PinHeader* h = reinterpret_cast<PinHeader*>(head);
+      h->magic = kPinMagic; h->map_bytes = (uint64_t)(body + 4096); h->registered = 1;
+      *out = b;
+      return AWQK_OK;
+    }
+    (void)cudaGetLastError();
+    (void)munmap(head, body + 4096);
+  }
+  // fallback: the runtime's own page-locked allocation (same contract, slower to obtain)
+  uint8_t* p = nullptr;
+  AWQK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p), bytes + 4096, cudaHostAllocPortable));
+  PinHeader* h = reinterpret_cast<PinHeader*>(p);
+  h->magic = kPinMagic; h->map_bytes = 0; h->registered = 0;
+  *out = p + 4096;
+  return AWQK_OK;
+}
+
+extern "C" int awqk_host_free_pinned(void* ptr) {
+  if (ptr == nullptr) return AWQK_OK;
+  uint8_t* b = static_cast<uint8_t*>(ptr);
+  PinHeader* h = reinterpret_cast<PinHeader*>(b - 4096);
+  if (h->magic != kPinMagic) return AWQK_E_BADARG;
+  if (h->registered) {
+    const size_t map_bytes = (size_t)h->map_bytes;
+    (void)cudaHostUnregister(b);
+    h->magic = 0;
+    (void)munmap(b - 4096, map_bytes);
+  } else {
+    h->magic = 0;
+    (void)cudaFreeHost(b - 4096);
+  }
+  return AWQK_OK;
+}
+
 extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* const* src, const int64_t* numel,
                                       int64_t row_len, int dtype, int group_size, int bits, int symmetric, int arith,
                                       int32_t* q_unpacked_host, uint32_t* q_packed_host, void* scales_f16_host,
@@ -437,7 +503,10 @@ extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* c
   const bool direct = is_pinned(q_unpacked_host) && is_pinned(q_packed_host) && is_pinned(scales_f16_host) &&
                       is_pinned(zp_host) && is_pinned(zp_packed_host);
   for (int b = 0; b < kBuf; ++b) {
-    if (p->h_in[b] == nullptr) AWQK_CUDA(cudaHostAlloc(&p->h_in[b], p->chunk_bytes, cudaHostAllocDefault));
+    if (p->h_in[b] == nullptr) {
+      const int rc = awqk_host_alloc_pinned(p->chunk_bytes, &p->h_in[b]);
+      if (rc != AWQK_OK) return rc;
+    }
     if (p->ev_h2d[b] == nullptr) AWQK_CUDA(cudaEventCreateWithFlags(&p->ev_h2d[b], cudaEventDisableTiming));
     if (q_unpacked_host != nullptr && p->d_qu[b] == nullptr)
       AWQK_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->d_qu[b]), p->elems_max * 4));
@@ -448,8 +517,9 @@ extern "C" int awqk_pipe_quant_gather(awqk_pipe* p, int n_tensors, const void* c
   }
   if (!direct && p->h_out_bytes < lay.total) {
     for (int b = 0; b < kBuf; ++b) {
-      if (p->h_out[b]) { AWQK_CUDA(cudaStreamSynchronize(p->s_out)); (void)cudaFreeHost(p->h_out[b]); p->h_out[b] = nullptr; }
-      AWQK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p->h_out[b]), lay.total, cudaHostAllocDefault));
+      if (p->h_out[b]) { AWQK_CUDA(cudaStreamSynchronize(p->s_out)); (void)awqk_host_free_pinned(p->h_out[b]); p->h_out[b] = nullptr; }
+      const int rc = awqk_host_alloc_pinned(lay.total, reinterpret_cast<void**>(&p->h_out[b]));
+      if (rc != AWQK_OK) return rc;
     }
     p->h_out_bytes = lay.total;
   }

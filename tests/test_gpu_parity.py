@@ -704,3 +704,35 @@ def test_quantize_routes_large_host_tensors_through_the_pipeline(native_lib, cud
     ragged = datagen.weights((4100, 300), "bf16", 4)
     assert mk()._quantize_host_pipelined(ragged, cuda_device, False, True) is None         # rows are not whole groups
     assert_quant_equal(mk(symmetric=False).quantize(ragged), O.group_quant_vec(ragged, 4, 128, False, True), "ragged")
+
+
+def test_native_pinned_staging_buffers(native_lib, cuda_device):
+    """awqk_host_alloc_pinned: page-locked in place (huge-page mapping + cudaHostRegister), usable for asynchronous
+    copies in both directions, 2 MiB aligned, returned to / reused from the process-wide cache, freed on eviction"""
+    import ctypes
+    from awq_quantizer import _native as N
+    nb = (8 << 20) + 4096
+    t = N.pinned_take(nb)
+    assert t.dtype == torch.uint8 and t.numel() == nb and t.is_pinned() and t.data_ptr() % (2 << 20) == 0
+    src = torch.arange(nb, dtype=torch.int64).to(torch.uint8)
+    t.copy_(src)
+    d = torch.empty(nb, dtype=torch.uint8, device=cuda_device)
+    d.copy_(t, non_blocking=True)
+    back = N.pinned_take(nb)
+    assert back.data_ptr() != t.data_ptr()
+    back.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+    assert torch.equal(back, src)
+    ptr = t.data_ptr()
+    N.pinned_give_back(t)
+    N.pinned_give_back(back)
+    again = N.pinned_take(nb)                       # same size: served from the cache
+    assert again.data_ptr() in (ptr, back.data_ptr())
+    N.pinned_give_back(again)
+    N.pinned_give_back(torch.empty(16, dtype=torch.uint8))      # foreign tensors are ignored
+    # raw ABI: allocate / free, bad pointers are refused
+    out = ctypes.c_void_p()
+    assert native_lib.awqk_host_alloc_pinned(1 << 20, ctypes.byref(out)) == 0 and out.value
+    assert native_lib.awqk_host_free_pinned(out) == 0
+    assert native_lib.awqk_host_alloc_pinned(0, ctypes.byref(out)) == -1
+    assert native_lib.awqk_host_free_pinned(None) == 0
