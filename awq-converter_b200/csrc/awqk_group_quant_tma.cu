@@ -945,7 +945,11 @@ int launch_group_quant_tma(const void* w, int dtype, int64_t n_elems, int g, int
 // ---- column-slab batches -----------------------------------------------------------------------------------
 // K % 1024 == 0, and the per-tile output strides (8 rows) below 2^32 bytes; anything else stays on the register path.
 bool group_quant_tma_cs_eligible(int64_t C, int64_t K) {
-  return C > 0 && C < ((int64_t)1 << 31) && K > 0 && K % kV2WarpTile == 0 && K <= ((int64_t)1 << 21);
+  if (!(C > 0 && C < ((int64_t)1 << 31) && K > 0 && K % kV2WarpTile == 0 && K <= ((int64_t)1 << 21))) return false;
+  // unit -> (row chunk, slab) uses a multiply-high division that is exact while (units of the tensor) x slabs < 2^32;
+  // the shortest units are 8 rows
+  const int64_t slabs = K / kV2WarpTile;
+  return ceil_div(C, 8) * slabs < ((int64_t)1 << 32) / slabs;
 }
 
 template <typename InT, int G, bool UNPACKED>

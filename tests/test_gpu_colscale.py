@@ -177,6 +177,38 @@ def test_colscale_batch_more_than_one_launch_and_fallbacks(native_lib, cuda_devi
     _batch_case(native_lib, N, cuda_device, shapes, "bf16", 128, False, unpacked=False)
 
 
+@pytest.mark.parametrize("want_zp,want_zq", [(False, True), (True, False), (False, False)])
+def test_colscale_batch_output_subsets(native_lib, cuda_device, want_zp, want_zq):
+    """launch-uniform output flags: packed zeros only (what the packed model path asks for), int32 zero points only,
+    neither -- and a batch that mixes tensors with different output sets (split into one launch per set)"""
+    from awq_quantizer import _native as N
+    dev = cuda_device
+    g = 128
+    shapes = [(40, 2048), (9, 1024), (130, 3072)]
+    items, keep, wants = [], [], []
+    for i, (C, K) in enumerate(shapes):
+        G = K // g
+        w = datagen.weights((C, K), "bf16", datagen.seed_of("csf", i, C, K))
+        s = _scales(K, 7 * i + 1)
+        wants.append(O.pack_result(O.quantize_scaled(w, s, 4, g, False)))
+        mixed_zp = want_zp or (i == 2 and not want_zq)            # third tensor of the (False, False) case differs on purpose
+        o = {"qp": torch.full((C, K // 8), 77, dtype=torch.int32, device=dev),
+             "s": torch.zeros((C, G), dtype=torch.float16, device=dev),
+             "z": torch.full((C, G), 77, dtype=torch.int32, device=dev) if mixed_zp else None,
+             "zq": torch.full((C, G // 8), 77, dtype=torch.int32, device=dev) if want_zq else None}
+        keep.append((w.to(dev), s.to(dev), o))
+        items.append((keep[-1][0], C, K, keep[-1][1], None, o["qp"], o["s"], o["z"], o["zq"]))
+    N.group_quant_batch(items, N.BF16, g, 4, False, N.ARITH_FP32, None)
+    torch.cuda.synchronize()
+    for (w, s, o), want in zip(keep, wants):
+        assert_same(o["qp"].cpu(), want["qweight"], "qweight")
+        assert_same(o["s"].cpu(), want["scales"], "scales")
+        if o["z"] is not None:
+            assert_same(o["z"].cpu(), want["zero_points"], "zero_points")
+        if o["zq"] is not None:
+            assert_same(o["zq"].cpu(), want["qzeros"], "qzeros")
+
+
 def test_colscale_batch_equals_single_calls(native_lib, cuda_device):
     """Llama-3-8B layer shapes (q, k, v, o, gate, up, down) in one launch == seven awqk_group_quant calls"""
     from awq_quantizer import _native as N
