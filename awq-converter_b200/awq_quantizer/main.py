@@ -70,7 +70,8 @@ def parse_args(argv=None) -> argparse.Namespace:
     p.add_argument("--config", type=str, help="YAML config (reference schema); CLI flags win over it")
     p.add_argument("--calibration_file", type=str,
                    help="safetensors file {weight name: activations [tokens, in_features]}: run the "
-                        "activation-aware alpha search (scale_method) for those weights")
+                        "activation-aware alpha search (scale_method) for those weights; __metadata__ entries "
+                        "'alias.<weight name>' = '<stored name>' let several weights share one stored tensor")
     p.add_argument("--n_grid", type=int, default=20, help="points of the alpha grid for --calibration_file")
     return p.parse_args(argv)
 
@@ -271,6 +272,35 @@ def _apply_config(args: argparse.Namespace, argv) -> None:
     args.skip_layers = list(cfg.get("quantization.skip_layers", []) or [])
 
 
+_ALIAS = "alias."
+
+
+def read_calibration_index(path: str) -> Dict[str, int]:
+    """header only: {weight name: calibration tokens}.  A calibration file maps weight names to activation tensors
+    [tokens, in_features]; linears that see the same input (q/k/v, gate/up) may share ONE stored tensor through
+    ``__metadata__`` entries ``alias.<weight name> = <stored tensor name>``."""
+    from safetensors import safe_open
+    with safe_open(path, framework="pt") as f:
+        tokens = {k: f.get_slice(k).get_shape()[0] for k in f.keys()}
+        for k, v in (f.metadata() or {}).items():
+            if k.startswith(_ALIAS) and v in tokens:
+                tokens[k[len(_ALIAS):]] = tokens[v]
+    return tokens
+
+
+def load_calibration(path: str) -> Dict[str, torch.Tensor]:
+    """{weight name: activations}; aliased weights get the SAME tensor object, so that the streamed search uploads
+    it once and computes its scale grid once"""
+    from safetensors import safe_open
+    from safetensors.torch import load_file
+    calib = load_file(path)
+    with safe_open(path, framework="pt") as f:
+        for k, v in (f.metadata() or {}).items():
+            if k.startswith(_ALIAS) and v in calib:
+                calib[k[len(_ALIAS):]] = calib[v]
+    return calib
+
+
 def select_tensors(index, skip_layers, logger=None):
     """main.py:243-253 on the header index: (quantizable names largest first, pass-through names).  Non-float,
     empty and numel < 128 tensors -- and those matching ``quantization.skip_layers`` (default_config.yaml:35) -- are
@@ -353,9 +383,7 @@ def _rank_work(args, logger, rank: int, world: int, local: int) -> dict:
         calib_tokens = {}
         if args.calibration_file and args.scale_method == "mse":
             try:                                         # header only: which weights will be searched, and over how many tokens
-                from safetensors import safe_open
-                with safe_open(args.calibration_file, framework="pt") as f:
-                    calib_tokens = {k: f.get_slice(k).get_shape()[0] for k in f.keys()}
+                calib_tokens = read_calibration_index(args.calibration_file)
             except Exception as e:
                 meta["error"] = f"Failed to read calibration file: {e}"
                 return meta
@@ -384,8 +412,7 @@ def _rank_work(args, logger, rank: int, world: int, local: int) -> dict:
             if args.scale_method != "mse":
                 logger.warning("--calibration_file is ignored: the activation-aware search belongs to scale_method=mse")
             else:
-                from safetensors.torch import load_file
-                calib = load_file(args.calibration_file)
+                calib = load_calibration(args.calibration_file)
                 logger.info(f"Loaded calibration activations for {len(calib)} tensors")
         lap("map_calibration")
 

@@ -262,3 +262,24 @@ def test_native_safetensors_writer_round_trip(tmp_path):
     assert meta["num_chunks"] == 12 and meta["files"] == [f"model_chunk_{c:04d}.safetensors" for c in range(12)]
     got = load_file(str(tmp_path / "many" / "model_chunk_0011.safetensors"))
     assert torch.equal(got["t22.qweight"], q["t22"]["qweight"])
+
+
+def test_calibration_file_aliases(tmp_path):
+    """several weights may share one stored activation tensor through __metadata__ aliases: the index reports tokens
+    for all of them and the loaded dict hands out the SAME tensor object (one upload, one scale grid)"""
+    from safetensors.torch import save_file
+    x = torch.randn(24, 64).to(torch.bfloat16)
+    y = torch.randn(8, 32).to(torch.bfloat16)
+    path = str(tmp_path / "calib.safetensors")
+    save_file({"l0.q_proj.weight": x, "l0.down_proj.weight": y}, path,
+              metadata={"alias.l0.k_proj.weight": "l0.q_proj.weight", "alias.l0.v_proj.weight": "l0.q_proj.weight",
+                        "alias.dangling": "missing", "comment": "ignored"})
+    idx = cli.read_calibration_index(path)
+    assert idx == {"l0.q_proj.weight": 24, "l0.down_proj.weight": 8, "l0.k_proj.weight": 24, "l0.v_proj.weight": 24}
+    calib = cli.load_calibration(path)
+    assert sorted(calib) == sorted(idx)
+    assert calib["l0.k_proj.weight"] is calib["l0.q_proj.weight"] and calib["l0.v_proj.weight"] is calib["l0.q_proj.weight"]
+    assert torch.equal(calib["l0.q_proj.weight"], x) and torch.equal(calib["l0.down_proj.weight"], y)
+    plain = str(tmp_path / "plain.safetensors")                 # files without metadata keep working
+    save_file({"w": x}, plain)
+    assert cli.read_calibration_index(plain) == {"w": 24} and list(cli.load_calibration(plain)) == ["w"]

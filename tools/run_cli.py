@@ -43,17 +43,19 @@ del shard
 argv = ["--model_id", src, "--output_dir", dst, "--log_level", "ERROR", "--chunk_size", "64"]
 calib_bytes = 0
 if args.search:                                   # {weight name: activations [T, K]} -- the CLI's calibration format
-    acts, cache = {}, {}
+    acts, cache, alias = {}, {}, {}
     for name, shape, ck in specs:
         if ck is None or len(shape) != 2:
             continue
         key = (ck, shape[1])
-        if key not in cache:
+        if key not in cache:                            # the first weight that sees this input stores it ...
             gain = torch.exp(torch.randn(shape[1], generator=gen, device=gdev))
-            cache[key] = (torch.randn((args.tokens, shape[1]), generator=gen, device=gdev) * gain).to(torch.bfloat16).cpu()
-        acts[name] = cache[key].clone()                 # (safetensors refuses tensors that share storage)
+            acts[name] = (torch.randn((args.tokens, shape[1]), generator=gen, device=gdev) * gain).to(torch.bfloat16).cpu()
+            cache[key] = name
+        else:                                           # ... the others refer to it (q/k/v, gate/up)
+            alias["alias." + name] = cache[key]
     calib_path = os.path.join(work, "calibration.safetensors")
-    save_file(acts, calib_path)
+    save_file(acts, calib_path, metadata=alias)
     calib_bytes = os.path.getsize(calib_path)
     del acts, cache
     argv += ["--calibration_file", calib_path]
