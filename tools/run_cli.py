@@ -78,7 +78,7 @@ out_bytes = sum(os.path.getsize(os.path.join(dst, f)) for f in os.listdir(dst))
 print(json.dumps({"workload": args.workload, "cli": "awq_quantizer " + " ".join(argv[4:]), "bf16_GB": total / 1e9,
                   "calibration_GB": calib_bytes / 1e9, "synthetic_checkpoint_written_in_s": round(t_gen, 1),
                   "tensors_quantized": meta["num_tensors"], "wall_s_first_run": round(runs[0], 3),
-                  "wall_s_second_run": round(runs[-1], 3) if len(runs) > 1 else None,
+                  "wall_s_second_run": round(runs[-1], 3) if len(runs) > 1 else None, "wall_s_all_runs": [round(r, 3) for r in runs],
                   "output_GB": out_bytes / 1e9, "timing_s_last_run": meta.get("timing_s_rank0"), "note": "load_tensors + quantize + save chunks, one process, 1 GPU"}))
 if not args.keep:
     shutil.rmtree(work, ignore_errors=True)
