@@ -180,6 +180,14 @@ def pinned_give_back(t) -> None:
         nb = _pin_live.pop(ptr, None)
         if nb is None:
             return                                  # not one of ours (e.g. torch's own pinned allocation)
+        if nb > _PIN_CACHE_BYTES // 2:              # too big to keep: it would push every staging slot out of the cache
+            drop.append(ptr)
+            nb = None
+    if nb is None:
+        for p in drop:
+            lib().awqk_host_free_pinned(p)
+        return
+    with _pin_lock:
         _pin_free.append((nb, ptr, t))
         total = sum(b for b, _, _ in _pin_free)
         while total > _PIN_CACHE_BYTES and len(_pin_free) > 1:

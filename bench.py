@@ -630,8 +630,20 @@ def e2e_leg(torch, dist, AWQQuantizer, model, dev, world, local, g, sym, n_grid,
     pinned = None
     if world == 1 and 2 * elems <= (24 << 30):          # sub-record: the same call on PINNED input tensors (what a
         try:                                            # loader that reads into page-locked memory would hand over)
+            from awq_quantizer import _native as N
             t0 = time.perf_counter()
-            pin_w = {n: t.pin_memory() for n, t in host_w.items()}
+            # one page-locked block for the whole model from awqk_host_alloc_pinned (huge pages, page-locked in place:
+            # ~1 s for 16 GB; torch's pin_memory() = cudaHostAlloc takes 13 s), tensors copied in by the native copy pool
+            offs, total = {}, 0
+            for n, t in host_w.items():
+                offs[n] = total
+                total += -(-t.numel() * t.element_size() // 256) * 256
+            block = N.pinned_take(total)
+            pin_w = {}
+            for n, t in host_w.items():
+                v = block[offs[n]:offs[n] + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+                N.host_copy(v, t)
+                pin_w[n] = v
             pin_s = time.perf_counter() - t0
             tp = []
             for it in range(3):
@@ -642,8 +654,12 @@ def e2e_leg(torch, dist, AWQQuantizer, model, dev, world, local, g, sym, n_grid,
                 tp.append(time.perf_counter() - t0)
                 del r2
             pinned = {"s_per_model": min(tp[1:]), "value": 2 * elems / min(tp[1:]) / 1e9, "unit": UNIT,
-                      "pinning_the_inputs_s": pin_s, "note": "no staging copy: the upload DMA reads the caller's tensors"}
+                      "pinning_the_inputs_s": pin_s,
+                      "note": "no staging copy: the upload DMA reads the caller's tensors (page-locked block from "
+                              "awqk_host_alloc_pinned + one copy of the model into it)"}
             del pin_w
+            N.pinned_give_back(block)
+            del block
         except Exception as e:
             pinned = {"error": str(e)[:120]}
     d2h = sum(v.numel() * v.element_size() for r in res.values() for v in r.values() if hasattr(v, "numel") and v.dim() > 0)
