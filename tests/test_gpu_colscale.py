@@ -235,3 +235,44 @@ def test_colscale_batch_equals_single_calls(native_lib, cuda_device):
         for k in a:
             assert torch.equal(a[k].view(torch.int32) if k != "s" else a[k].view(torch.int16),
                                b[k].view(torch.int32) if k != "s" else b[k].view(torch.int16)), (i, k)
+
+
+def test_colscale_batch_randomized_vs_register_path(native_lib, cuda_device):
+    """randomized batches (1..31 tensors, heights 1..3000, 1..8 slabs, every group size, both symmetries) against the
+    independent register-path kernel (group_quant_flat with col_scale), which awqk_group_quant selects when q_packed is
+    only 8-byte aligned -- two implementations of the same arithmetic, compared on ~10^8 elements"""
+    import random
+    from awq_quantizer import _native as N
+    dev = cuda_device
+    rnd = random.Random(2024)
+    for case in range(12):
+        g = rnd.choice([32, 64, 128])
+        sym = rnd.random() < 0.3
+        n = rnd.choice([1, 2, 5, 17, 31])
+        items, ref = [], []
+        for i in range(n):
+            C = rnd.choice([1, 7, 8, 9, 63, 250, rnd.randint(1, 3000)])
+            K = 1024 * rnd.randint(1, 8)
+            G = K // g
+            gen = torch.Generator(device=dev).manual_seed(1000 * case + i)
+            w = (torch.randn((C, K), generator=gen, device=dev) * (0.02 if i % 3 else 3.0)).to(torch.bfloat16)
+            if i % 5 == 0:
+                w[:, :g] = w[:, :g].abs() + 0.01                       # all-positive groups: clamped zero points
+            s = torch.exp(0.7 * torch.randn(K, generator=gen, device=dev)).float()
+            out = {"qp": torch.zeros((C, K // 8), dtype=torch.int32, device=dev), "s": torch.zeros((C, G), dtype=torch.float16, device=dev),
+                   "z": torch.zeros((C, G), dtype=torch.int32, device=dev), "zq": torch.zeros((C, -(-G // 8)), dtype=torch.int32, device=dev)}
+            items.append((w, C, K, s, None, out["qp"], out["s"], out["z"], out["zq"]))
+            # reference: same call with a q_packed pointer that is 8- but not 16-byte aligned -> register path
+            buf = torch.zeros(C * (K // 8) + 4, dtype=torch.int32, device=dev)
+            qp = buf[2:2 + C * (K // 8)].view(C, K // 8)
+            assert qp.data_ptr() % 16 == 8
+            r = {"qp": qp, "s": torch.zeros_like(out["s"]), "z": torch.zeros_like(out["z"]), "zq": torch.zeros_like(out["zq"])}
+            N.check(native_lib.awqk_group_quant(w.data_ptr(), N.BF16, C, K, g, 4, int(sym), N.ARITH_FP32, None, qp.data_ptr(),
+                                                r["s"].data_ptr(), r["z"].data_ptr(), r["zq"].data_ptr(), s.data_ptr(), None))
+            ref.append((out, r))
+        N.group_quant_batch(items, N.BF16, g, 4, sym, N.ARITH_FP32, None)
+        torch.cuda.synchronize()
+        for i, (out, r) in enumerate(ref):
+            for k in ("qp", "z", "zq"):
+                assert torch.equal(out[k], r[k]), (case, i, k, items[i][1:3], g, sym)
+            assert torch.equal(out["s"].view(torch.int16), r["s"].view(torch.int16)), (case, i, "scales")
