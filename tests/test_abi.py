@@ -144,3 +144,19 @@ def test_batch_plan_rejects_bad_arguments(native_lib):
     assert _plan(native_lib, [(16, 1024)] * 32)[0] == -1       # more than 31 tensors per launch
     assert _plan(native_lib, [(16, 1024)], sms=0)[0] == -1
     assert _plan(native_lib, [(16, 1024)], g=48)[0] == -1
+
+
+def test_quant_item_struct_layout_matches_header(tmp_path):
+    """the ctypes mirror of awqk_quant_item (used by awqk_group_quant_batch) has the size and field offsets the C
+    compiler gives the struct declared in include/awqk.h"""
+    from awq_quantizer import _native
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "awqk.h"\n'
+                   'int main(void) { printf("%zu", sizeof(awqk_quant_item));\n'
+                   + "".join(f'  printf(" %zu", offsetof(awqk_quant_item, {f}));\n' for f, _ in _native.QuantItem._fields_)
+                   + "  return 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_native.QuantItem)] + [getattr(_native.QuantItem, f).offset for f, _ in _native.QuantItem._fields_]
+    assert got == want, (got, want)
