@@ -736,3 +736,32 @@ def test_native_pinned_staging_buffers(native_lib, cuda_device):
     assert native_lib.awqk_host_free_pinned(out) == 0
     assert native_lib.awqk_host_alloc_pinned(0, ctypes.byref(out)) == -1
     assert native_lib.awqk_host_free_pinned(None) == 0
+
+
+@pytest.mark.parametrize("sym", [False, True])
+def test_autoawq_export_is_read_correctly_by_vllm(native_lib, cuda_device, sym):
+    """The AutoAWQ / vLLM GEMM layout written by quantization/export.py is PINNED against a third-party consumer:
+    vLLM's own AWQ de-quantization kernel (vllm._custom_ops.awq_dequantize, the kernel its AWQ linear layers use) must
+    reconstruct, from the exported qweight [K, C/8] / qzeros [G, C/8] / scales [G, C], exactly the weight this
+    repo's de-quantizer (the reference's arithmetic, K4) reconstructs from the packed K1 result."""
+    try:
+        from vllm import _custom_ops as vops
+    except Exception as e:                                        # pragma: no cover
+        pytest.skip(f"vllm is not importable here: {e}")
+    from awq_quantizer.quantization import AWQQuantizer
+    from awq_quantizer.quantization.export import to_autoawq_gemm
+    C, K = 256, 1024
+    w = datagen.weights((C, K), "fp16", 77)
+    qz = AWQQuantizer(bits=4, group_size=128, symmetric=sym, device="cuda:0", logger_level="ERROR")
+    res = qz.quantize(w, pack=True)
+    exp = to_autoawq_gemm(res, device=cuda_device)
+    try:
+        back = vops.awq_dequantize(exp["qweight"].to(cuda_device), exp["scales"].to(cuda_device),
+                                   exp["qzeros"].to(cuda_device), 0, 0, 0)
+    except Exception as e:                                        # pragma: no cover
+        pytest.skip(f"vllm's awq_dequantize is not usable on this box: {e}")
+    torch.cuda.synchronize()
+    assert back.shape == (K, C) and back.dtype == torch.float16
+    mine = qz.dequantize(res)                                     # fp32 [C, K], fp16 multiply like the reference
+    got = back.float().t().cpu()
+    assert torch.equal(got, mine), float((got - mine).abs().max())
