@@ -765,3 +765,14 @@ def test_autoawq_export_is_read_correctly_by_vllm(native_lib, cuda_device, sym):
     mine = qz.dequantize(res)                                     # fp32 [C, K], fp16 multiply like the reference
     got = back.float().t().cpu()
     assert torch.equal(got, mine), float((got - mine).abs().max())
+    # and vLLM's AWQ GEMM (the kernel that serves such a checkpoint) computes x . W^T with those weights
+    try:
+        x = datagen.weights((16, K), "fp16", 5, std=1.0).to(cuda_device)
+        y = vops.awq_gemm(x, exp["qweight"].to(cuda_device), exp["scales"].to(cuda_device), exp["qzeros"].to(cuda_device), 8)
+    except Exception as e:                                        # pragma: no cover
+        pytest.skip(f"vllm's awq_gemm is not usable on this box: {e}")
+    torch.cuda.synchronize()
+    want = x.float() @ mine.to(cuda_device).t()
+    assert y.shape == (16, C)
+    err = float((y.float() - want).abs().max() / want.abs().max())
+    assert err < 2e-2, err                                        # fp16 accumulation inside the kernel
