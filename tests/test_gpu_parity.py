@@ -713,7 +713,8 @@ def test_native_pinned_staging_buffers(native_lib, cuda_device):
     from awq_quantizer import _native as N
     nb = (8 << 20) + 4096
     t = N.pinned_take(nb)
-    assert t.dtype == torch.uint8 and t.numel() == nb and t.is_pinned() and t.data_ptr() % (2 << 20) == 0
+    assert t.dtype == torch.uint8 and t.numel() == nb and t.is_pinned()
+    assert t.data_ptr() % 4096 == 0                 # (2 MiB on the cudaHostRegister path, a page on the cudaHostAlloc fallback)
     src = torch.arange(nb, dtype=torch.int64).to(torch.uint8)
     t.copy_(src)
     d = torch.empty(nb, dtype=torch.uint8, device=cuda_device)
